@@ -1,0 +1,184 @@
+"""Device PBRCompositor (mirror of gui/dplug/gui/legacypbr.d:67-266 and ICompositor, compositor.d:29-69)."""
+import ctypes as C
+import numpy as np
+from . import _lib
+from .mipmap import Mipmap, RGBA8, L16
+from .boxlist import tileAreas
+
+PBR_TILE_MAX_WIDTH = 64   # gui/dplug/gui/graphics.d:59
+PBR_TILE_MAX_HEIGHT = 64  # gui/dplug/gui/graphics.d:60
+
+DIFFUSE, MATERIAL, DEPTH = 0, 1, 2
+PF_RGBA8, PF_BGRA8, PF_ARGB8 = 0, 1, 2
+
+
+def default_params():
+    p = _lib.params()
+    _lib.lib().b2pbr_default_params(C.byref(p))
+    return p
+
+
+def _ref(arr):
+    return _lib.imageref(arr.shape[1], arr.shape[0], arr.strides[0], arr.ctypes.data)
+
+
+class PBRCompositor:
+    """`PBRCompositor(device)`; owns the device twins of the maps GUIGraphics lends to compositeTile."""
+
+    PASS_NORMAL, PASS_AO, PASS_OBLIQUE_SHADOW, PASS_DIRECTIONAL = 0, 1, 2, 3
+    PASS_SPECULAR, PASS_SKYBOX, PASS_EMISSIVE, PASS_CLAMP = 4, 5, 6, 7
+
+    def __init__(self, device=0, band=None):
+        self._l = _lib.lib()
+        h = C.c_void_p()
+        if band is None:
+            _lib.check(self._l.b2pbr_create(C.byref(h), device))
+        else:
+            _lib.check(self._l.b2pbr_create_band(C.byref(h), device, band[0], band[1]))
+        self._h = h
+        self.device = device
+        self.width = self.height = 0
+
+    def close(self):
+        if self._h:
+            self._l.b2pbr_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_stream(self, cuda_stream):
+        _lib.check(self._l.b2pbr_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    # --- ICompositor -------------------------------------------------------------------------
+    def resizeBuffers(self, width, height, areaMaxWidth=PBR_TILE_MAX_WIDTH, areaMaxHeight=PBR_TILE_MAX_HEIGHT):
+        _lib.check(self._l.b2pbr_resize(self._h, width, height, areaMaxWidth, areaMaxHeight))
+        self.width, self.height = width, height
+
+    def compositeTile(self, wfb, areas, diffuseMap=None, materialMap=None, depthMap=None, updateRects=None):
+        """ICompositor.compositeTile.  With numpy level-0 images this is the host drop-in (upload dirty rects,
+        regenerate device mips, composite, copy `areas` back into `wfb`); with device `Mipmap`s (or None = the
+        compositor's own twins) it composites device-resident data and `wfb` may be None."""
+        n = len(areas)
+        arr = _lib.boxes(areas)
+        if isinstance(diffuseMap, np.ndarray):
+            upd = _lib.boxes(updateRects) if updateRects is not None else None
+            _lib.check(self._l.b2pbr_composite_tile_host(self._h, _ref(wfb), arr, n, upd, 0 if updateRects is None else len(updateRects),
+                                                         _ref(diffuseMap), _ref(materialMap), _ref(depthMap)))
+            return wfb
+        hd = diffuseMap.handle if diffuseMap is not None else None
+        hm = materialMap.handle if materialMap is not None else None
+        hz = depthMap.handle if depthMap is not None else None
+        _lib.check(self._l.b2pbr_composite_tile(self._h, arr, n, hd, hm, hz))
+        if wfb is not None:
+            self.download(areas, out=wfb)
+        return wfb
+
+    # --- legacy setters, legacypbr.d:75-123 -----------------------------------------------------
+    def params(self):
+        p = _lib.params()
+        _lib.check(self._l.b2pbr_get_params(self._h, C.byref(p)))
+        return p
+
+    def set_params(self, p):
+        _lib.check(self._l.b2pbr_set_params(self._h, C.byref(p)))
+
+    def _set(self, name, value):
+        p = self.params()
+        if isinstance(value, (tuple, list, np.ndarray)):
+            setattr(p, name, (C.c_float * 3)(*[float(v) for v in value]))
+        else:
+            setattr(p, name, value)
+        self.set_params(p)
+
+    def light1Color(self, c): self._set("light1_color", c)
+    def light2Dir(self, d): self._set("light2_dir", d)
+    def light2Color(self, c): self._set("light2_color", c)
+    def light3Dir(self, d): self._set("light3_dir", d)
+    def light3Color(self, c): self._set("light3_color", c)
+    def skyboxAmount(self, a): self._set("skybox_amount", float(a))
+    def ambientLight(self, a): self._set("ambient_light", float(a))
+    def tonemapThreshold(self, v): self._set("tonemap_threshold", float(v))
+    def tonemapRatio(self, v): self._set("tonemap_ratio", float(v))
+
+    def setPassActive(self, index, active):
+        """getPass(index).setActive(active) — compositor.d:170-173,222-225."""
+        p = self.params()
+        m = p.pass_active_mask
+        p.pass_active_mask = (m | (1 << index)) if active else (m & ~(1 << index))
+        self.set_params(p)
+
+    def setSkybox(self, image):
+        """PassSkyboxReflections.setSkybox — legacypbr.d:861-870."""
+        if image is None:
+            _lib.check(self._l.b2pbr_set_skybox(self._h, None, 0, 0, 0))
+            return
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        _lib.check(self._l.b2pbr_set_skybox(self._h, image.ctypes.data_as(C.c_void_p), image.shape[1], image.shape[0], image.strides[0]))
+
+    # --- device twins -------------------------------------------------------------------------
+    def map(self, which):
+        h = self._l.b2pbr_map(self._h, which)
+        if not h:
+            raise _lib.B2Error("map before resizeBuffers")
+        return Mipmap(RGBA8 if which != DEPTH else L16, 0, 0, 0, _handle=h)
+
+    @property
+    def diffuseMap(self): return self.map(DIFFUSE)
+    @property
+    def materialMap(self): return self.map(MATERIAL)
+    @property
+    def depthMap(self): return self.map(DEPTH)
+
+    def skyboxMap(self):
+        h = self._l.b2pbr_skybox(self._h)
+        return Mipmap(RGBA8, 0, 0, 0, _handle=h) if h else None
+
+    # --- GUIGraphics slice ----------------------------------------------------------------------
+    def regenerateMipmaps(self, rects):
+        """GUIGraphics.regenerateMipmaps — gui/dplug/gui/graphics.d:1354-1423."""
+        _lib.check(self._l.b2pbr_regenerate_mipmaps(self._h, _lib.boxes(rects), len(rects)))
+
+    def compositeGUI(self, rectsToCompositeDisjointed, wfb=None):
+        """GUIGraphics.compositeGUI — gui/dplug/gui/graphics.d:1338-1349."""
+        tiles = tileAreas(rectsToCompositeDisjointed, PBR_TILE_MAX_WIDTH, PBR_TILE_MAX_HEIGHT)
+        return self.compositeTile(wfb, tiles)
+
+    def compositeRaw(self, areas):
+        """SimpleRawCompositor — compositor.d:260-298."""
+        _lib.check(self._l.b2pbr_composite_raw(self._h, _lib.boxes(areas), len(areas)))
+
+    def download(self, rects=None, out=None, pixelFormat=None):
+        if out is None:
+            out = np.zeros((self.height, self.width, 4), dtype=np.uint8)
+        if rects is None:
+            rects = [(0, 0, self.width, self.height)]
+        arr = _lib.boxes(rects)
+        if pixelFormat is None:
+            _lib.check(self._l.b2pbr_download(self._h, out.ctypes.data_as(C.c_void_p), out.strides[0], arr, len(rects)))
+        else:
+            _lib.check(self._l.b2pbr_download_swizzled(self._h, pixelFormat, out.ctypes.data_as(C.c_void_p), out.strides[0], arr, len(rects)))
+        return out
+
+    def sync(self):
+        _lib.check(self._l.b2pbr_sync(self._h))
+
+    def profileEnable(self, on=True):
+        _lib.check(self._l.b2pbr_profile_enable(self._h, 1 if on else 0))
+
+    def traceJSON(self):
+        need = C.c_size_t()
+        _lib.check(self._l.b2pbr_trace_json(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _lib.check(self._l.b2pbr_trace_json(self._h, buf, need.value, None))
+        return buf.value.decode()
+
+    def kernelLaunches(self):
+        return int(self._l.b2pbr_kernel_launches(self._h))

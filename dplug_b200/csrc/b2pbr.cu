@@ -1,0 +1,759 @@
+// libb2pbr — host runtime and C ABI (include/b2pbr.h) of the B200 PBR compositor.
+//
+// Owns the device twins of the reference's OwnedImage / Mipmap buffers (graphics/dplug/graphics/image.d,
+// mipmap.d), the dirty-rectangle tile scheduler (gui/dplug/gui/boxlist.d, graphics.d:1338-1423) and the
+// kernel launches.  There is no CPU implementation of any pixel work in this library: if CUDA is not
+// usable every entry point that would touch pixels fails with B2_ERR_NO_DEVICE / B2_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/b2pbr.h"
+#include "common.cuh"
+#include "host_rects.hpp"
+
+namespace b2 {
+// kernels (mip_kernels.cu, pbr_exact.cu, pbr_fast.cu)
+void launch_box_rgba(const DevLevel& dst, const DevLevel& src, Box r, bool premul, cudaStream_t s);
+void launch_box_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
+void launch_cubic_rgba(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
+void launch_cubic_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
+void launch_copy_diffuse(const DevLevel& dst, const DevLevel& src, const Box* boxes, int n, int grid, cudaStream_t s);
+void launch_swizzle(const DevLevel& dst, const DevLevel& src, Box box, int pf, cudaStream_t s);
+void launch_pbr_exact(const PbrArgs& args, int gridBlocks, cudaStream_t stream);
+void launch_sample(const DevLevel* levels, int nLevels, int color, int kind, int n, const float* lvl, const float* x,
+                   const float* y, float* out4, cudaStream_t stream);
+}  // namespace b2
+
+using namespace b2;
+
+static const uint32_t kRsqrtssTable[2048] = {
+#include "rsqrtss_table.inc"
+};
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(B2_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+    } while (0)
+
+static inline Box toBox(const b2_box2i& b) { return Box{b.min_x, b.min_y, b.max_x, b.max_y}; }
+static inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ================================================================================================ b2mip
+struct b2mip {
+    int device = 0, color = 0, elem = 4;
+    int W = 0, H = 0;
+    int bandY0 = 0, bandY1 = 0, haloUp = 0, haloDown = 0;  // level-0 rows owned / stored around them
+    std::vector<DevLevel> levels;
+    uint8_t* alloc = nullptr;
+    size_t allocBytes = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    uint64_t launches = 0;
+};
+
+static int countLevels(int maxLevel, int w, int h) {  // mipmap.d:83-94
+    int needed = 0;
+    for (; needed <= maxLevel; ++needed) {
+        if (w == 0 || h == 0) break;
+        w >>= 1; h >>= 1;
+    }
+    return needed;
+}
+
+static int mipAllocate(b2mip* m, int maxLevel) {
+    const int n = countLevels(maxLevel, m->W, m->H);
+    m->levels.resize(n);
+    const int sy0 = m->bandY0 - m->haloUp < 0 ? 0 : m->bandY0 - m->haloUp;
+    const int sy1 = m->bandY1 + m->haloDown > m->H ? m->H : m->bandY1 + m->haloDown;
+    const bool whole = (sy0 == 0 && sy1 == m->H);
+    size_t total = 0;
+    std::vector<size_t> offs(n);
+    int w = m->W, h = m->H;
+    for (int l = 0; l < n; ++l) {
+        DevLevel& L = m->levels[l];
+        L.w = w; L.h = h;
+        L.pitch = (int)alignUp((size_t)w * m->elem, 128);
+        if (whole) { L.y0 = 0; L.rows = h; }
+        else {
+            int lo = (sy0 >> l) - 2, hi = ((sy1 + (1 << l) - 1) >> l) + 2;
+            if (lo < 0) lo = 0;
+            if (hi > h) hi = h;
+            if (hi < lo) hi = lo;
+            L.y0 = lo; L.rows = hi - lo;
+        }
+        offs[l] = total;
+        total += alignUp((size_t)L.pitch * (size_t)(L.rows > 0 ? L.rows : 1), 256);
+        w >>= 1; h >>= 1;
+    }
+    if (total == 0) total = 256;
+    CU(cudaMalloc((void**)&m->alloc, total));
+    m->allocBytes = total;
+    CU(cudaMemsetAsync(m->alloc, 0, total, m->stream));
+    for (int l = 0; l < n; ++l) m->levels[l].base = m->alloc + offs[l];
+    return B2_OK;
+}
+
+static int mipCreate(b2mip** out, int device, int color, int maxLevel, int w, int h, int y0, int y1, int up, int down) {
+    if (!out || w < 0 || h < 0 || maxLevel < 0 || (color != B2_COLOR_RGBA8 && color != B2_COLOR_L16))
+        return fail(B2_ERR_INVALID, "b2mip_create: bad arguments");
+    if (y0 < 0 || y1 > h || y0 > y1) return fail(B2_ERR_INVALID, "b2mip_create: bad band");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(B2_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(B2_ERR_INVALID, "bad device index");
+    CU(cudaSetDevice(device));
+    b2mip* m = new b2mip();
+    m->device = device; m->color = color; m->elem = (color == B2_COLOR_RGBA8) ? 4 : 2;
+    m->W = w; m->H = h; m->bandY0 = y0; m->bandY1 = y1; m->haloUp = up; m->haloDown = down;
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) { delete m; return fail(B2_ERR_CUDA, "cudaStreamCreate failed"); }
+    m->ownStream = true;
+    int rc = mipAllocate(m, maxLevel);
+    if (rc != B2_OK) { if (m->alloc) cudaFree(m->alloc); cudaStreamDestroy(m->stream); delete m; return rc; }
+    *out = m;
+    return B2_OK;
+}
+
+static int mipCheckRect(const b2mip* m, int level, const b2_box2i& r, const char* who) {
+    if (level < 0 || level >= (int)m->levels.size()) return fail(B2_ERR_INVALID, std::string(who) + ": level out of range");
+    const DevLevel& L = m->levels[level];
+    if (!boxSorted(r) || r.min_x < 0 || r.min_y < 0 || r.max_x > L.w || r.max_y > L.h)
+        return fail(B2_ERR_INVALID, std::string(who) + ": rectangle outside the level");
+    if (!boxEmpty(r) && (r.min_y < L.y0 || r.max_y > L.y0 + L.rows))
+        return fail(B2_ERR_INVALID, std::string(who) + ": rectangle outside the rows stored by this band");
+    return B2_OK;
+}
+
+static int mipGenerateLevel(b2mip* m, int level, int quality, b2_box2i r) {
+    if (level < 1 || level >= (int)m->levels.size()) return fail(B2_ERR_INVALID, "generateLevel: level out of range");
+    int rc = mipCheckRect(m, level, r, "generateLevel");
+    if (rc) return rc;
+    if (boxEmpty(r)) return B2_OK;
+    const DevLevel& dst = m->levels[level];
+    const DevLevel& src = m->levels[level - 1];
+    // the source rows a destination row needs must be stored too (only relevant for row bands)
+    {
+        int lo = quality == B2_QUALITY_CUBIC ? 2 * r.min_y - 1 : 2 * r.min_y;
+        int hi = quality == B2_QUALITY_CUBIC ? 2 * (r.max_y - 1) + 2 : 2 * (r.max_y - 1) + 1;
+        if (lo < 0) lo = 0;
+        if (hi > src.h - 1) hi = src.h - 1;
+        if (lo < src.y0 || hi >= src.y0 + src.rows) return fail(B2_ERR_INVALID, "generateLevel: source rows outside the band's halo");
+    }
+    CU(cudaSetDevice(m->device));
+    if (m->color == B2_COLOR_RGBA8) {
+        if (quality == B2_QUALITY_BOX) launch_box_rgba(dst, src, toBox(r), false, m->stream);
+        else if (quality == B2_QUALITY_BOX_ALPHACOV_PREMUL) launch_box_rgba(dst, src, toBox(r), true, m->stream);
+        else if (quality == B2_QUALITY_CUBIC) launch_cubic_rgba(dst, src, toBox(r), m->stream);
+        else return fail(B2_ERR_INVALID, "generateLevel: unknown quality");
+    } else {
+        if (quality == B2_QUALITY_BOX) launch_box_l16(dst, src, toBox(r), m->stream);
+        else if (quality == B2_QUALITY_CUBIC) launch_cubic_l16(dst, src, toBox(r), m->stream);
+        else return fail(B2_ERR_INVALID, "generateLevel: boxAlphaCovIntoPremul is RGBA-only (mipmap.d:594-595)");
+    }
+    m->launches++;
+    CU(cudaGetLastError());
+    return B2_OK;
+}
+
+extern "C" {
+
+const char* b2_last_error(void) { return g_err.c_str(); }
+int b2_abi_version(void) { return B2PBR_ABI_VERSION; }
+int b2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int b2mip_create(b2mip** out, int device, int color, int max_level, int w, int h) {
+    return mipCreate(out, device, color, max_level, w, h, 0, h, 0, 0);
+}
+int b2mip_create_band(b2mip** out, int device, int color, int max_level, int w, int h, int y0, int y1, int halo_up, int halo_down) {
+    return mipCreate(out, device, color, max_level, w, h, y0, y1, halo_up, halo_down);
+}
+void b2mip_destroy(b2mip* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->alloc) cudaFree(m->alloc);
+    if (m->ownStream && m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+int b2mip_set_stream(b2mip* m, void* s) {
+    if (!m) return fail(B2_ERR_INVALID, "null mip");
+    if (m->ownStream && m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+    m->stream = (cudaStream_t)s;
+    m->ownStream = false;
+    return B2_OK;
+}
+int b2mip_num_levels(const b2mip* m) { return m ? (int)m->levels.size() : 0; }
+int b2mip_width(const b2mip* m) { return m ? m->W : 0; }
+int b2mip_height(const b2mip* m) { return m ? m->H : 0; }
+int b2mip_level(const b2mip* m, int level, b2_imageref* out, int* first_row) {
+    if (!m || !out || level < 0 || level >= (int)m->levels.size()) return fail(B2_ERR_INVALID, "b2mip_level: bad arguments");
+    const DevLevel& L = m->levels[level];
+    out->w = L.w; out->h = L.h; out->pitch = (size_t)L.pitch; out->pixels = L.base;
+    if (first_row) *first_row = L.y0;
+    return B2_OK;
+}
+
+int b2mip_upload(b2mip* m, int level, const void* host, size_t host_pitch, const b2_box2i* rects, int n) {
+    if (!m || !host || (n > 0 && !rects)) return fail(B2_ERR_INVALID, "b2mip_upload: bad arguments");
+    CU(cudaSetDevice(m->device));
+    for (int k = 0; k < n; ++k) {
+        int rc = mipCheckRect(m, level, rects[k], "b2mip_upload");
+        if (rc) return rc;
+        if (boxEmpty(rects[k])) continue;
+        const DevLevel& L = m->levels[level];
+        const b2_box2i& r = rects[k];
+        CU(cudaMemcpy2DAsync(L.base + (size_t)(r.min_y - L.y0) * L.pitch + (size_t)r.min_x * m->elem, (size_t)L.pitch,
+                             (const uint8_t*)host + (size_t)r.min_y * host_pitch + (size_t)r.min_x * m->elem, host_pitch,
+                             (size_t)boxW(r) * m->elem, (size_t)boxH(r), cudaMemcpyHostToDevice, m->stream));
+    }
+    return B2_OK;
+}
+int b2mip_download(b2mip* m, int level, void* host, size_t host_pitch, const b2_box2i* rects, int n) {
+    if (!m || !host || (n > 0 && !rects)) return fail(B2_ERR_INVALID, "b2mip_download: bad arguments");
+    CU(cudaSetDevice(m->device));
+    for (int k = 0; k < n; ++k) {
+        int rc = mipCheckRect(m, level, rects[k], "b2mip_download");
+        if (rc) return rc;
+        if (boxEmpty(rects[k])) continue;
+        const DevLevel& L = m->levels[level];
+        const b2_box2i& r = rects[k];
+        CU(cudaMemcpy2DAsync((uint8_t*)host + (size_t)r.min_y * host_pitch + (size_t)r.min_x * m->elem, host_pitch,
+                             L.base + (size_t)(r.min_y - L.y0) * L.pitch + (size_t)r.min_x * m->elem, (size_t)L.pitch,
+                             (size_t)boxW(r) * m->elem, (size_t)boxH(r), cudaMemcpyDeviceToHost, m->stream));
+    }
+    CU(cudaStreamSynchronize(m->stream));
+    return B2_OK;
+}
+
+int b2mip_generate_level(b2mip* m, int level, int quality, b2_box2i r) {
+    if (!m) return fail(B2_ERR_INVALID, "null mip");
+    return mipGenerateLevel(m, level, quality, r);
+}
+int b2mip_generate_next_level(b2mip* m, int quality, b2_box2i prev, int level, b2_box2i* out_rect) {
+    if (!m || level < 1 || level >= (int)m->levels.size()) return fail(B2_ERR_INVALID, "generateNextLevel: level out of range");
+    const DevLevel& P = m->levels[level - 1];
+    b2_box2i r = impactOnNextLevel(quality, prev, P.w, P.h);
+    if (out_rect) *out_rect = r;
+    return mipGenerateLevel(m, level, quality, r);
+}
+int b2mip_generate_mipmaps(b2mip* m, int quality) {
+    if (!m) return fail(B2_ERR_INVALID, "null mip");
+    b2_box2i r{0, 0, m->W, m->H};
+    for (int level = 1; level < (int)m->levels.size(); ++level) {
+        if (level >= 3 && quality == B2_QUALITY_BOX) quality = B2_QUALITY_CUBIC;  // mipmap.d:522-524
+        int rc = b2mip_generate_next_level(m, quality, r, level, &r);
+        if (rc) return rc;
+    }
+    return B2_OK;
+}
+int b2mip_generate_chain(b2mip* m, int first_quality, int cubic_from_level) {
+    if (!m) return fail(B2_ERR_INVALID, "null mip");
+    b2_box2i r{0, 0, m->W, m->H};
+    for (int level = 1; level < (int)m->levels.size(); ++level) {
+        int q = level >= cubic_from_level ? B2_QUALITY_CUBIC : (level == 1 ? first_quality : B2_QUALITY_BOX);
+        int rc = b2mip_generate_next_level(m, q, r, level, &r);
+        if (rc) return rc;
+    }
+    return B2_OK;
+}
+int b2mip_sample(b2mip* m, int kind, int n, const float* level, const float* x, const float* y, float* out4) {
+    if (!m || n < 0 || kind < 0 || kind > 2) return fail(B2_ERR_INVALID, "b2mip_sample: bad arguments");
+    if (n == 0) return B2_OK;
+    CU(cudaSetDevice(m->device));
+    float *dl = nullptr, *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    DevLevel* dlev = nullptr;
+    CU(cudaMalloc((void**)&dl, sizeof(float) * n));
+    CU(cudaMalloc((void**)&dx, sizeof(float) * n));
+    CU(cudaMalloc((void**)&dy, sizeof(float) * n));
+    CU(cudaMalloc((void**)&dout, sizeof(float) * 4 * n));
+    CU(cudaMalloc((void**)&dlev, sizeof(DevLevel) * m->levels.size()));
+    CU(cudaMemcpyAsync(dl, level, sizeof(float) * n, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(dx, x, sizeof(float) * n, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(dy, y, sizeof(float) * n, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(dlev, m->levels.data(), sizeof(DevLevel) * m->levels.size(), cudaMemcpyHostToDevice, m->stream));
+    launch_sample(dlev, (int)m->levels.size(), m->color, kind, n, dl, dx, dy, dout, m->stream);
+    m->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out4, dout, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    cudaFree(dl); cudaFree(dx); cudaFree(dy); cudaFree(dout); cudaFree(dlev);
+    return B2_OK;
+}
+int b2mip_sync(b2mip* m) {
+    if (!m) return fail(B2_ERR_INVALID, "null mip");
+    CU(cudaStreamSynchronize(m->stream));
+    return B2_OK;
+}
+uint64_t b2mip_kernel_launches(const b2mip* m) { return m ? m->launches : 0; }
+
+b2_box2i b2_impact_on_next_level(int quality, b2_box2i area, int w, int h) { return impactOnNextLevel(quality, area, w, h); }
+int b2_tile_areas(const b2_box2i* areas, int n, int max_w, int max_h, b2_box2i* out, int cap) {
+    if (max_w <= 0 || max_h <= 0) return 0;
+    std::vector<b2_box2i> v;
+    tileAreas(areas, n, max_w, max_h, v);
+    for (int i = 0; i < (int)v.size() && i < cap; ++i) out[i] = v[i];
+    return (int)v.size();
+}
+int b2_remove_overlapping_areas(b2_box2i* boxes, int n, b2_box2i* out, int cap) {
+    std::vector<b2_box2i> in(boxes, boxes + n), f;
+    removeOverlappingAreas(in, f);
+    for (int i = 0; i < (int)f.size() && i < cap; ++i) out[i] = f[i];
+    return (int)f.size();
+}
+b2_box2i b2_grow_rect(b2_box2i rect, int margin, int width, int height) { return growRect(rect, margin, width, height); }
+
+int b2_host_register(void* ptr, size_t bytes) {
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return B2_OK;
+}
+int b2_host_unregister(void* ptr) {
+    CU(cudaHostUnregister(ptr));
+    return B2_OK;
+}
+
+}  // extern "C"
+
+// ================================================================================================ b2pbr
+struct TraceEvent { std::string name; cudaEvent_t beg, end; };
+
+struct b2pbr {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    int W = 0, H = 0, tileW = 64, tileH = 64;
+    bool banded = false;
+    int bandY0 = 0, bandY1 = 0;
+    b2mip *diffuse = nullptr, *material = nullptr, *depth = nullptr, *sky = nullptr;
+    DevLevel out{}; uint8_t* outAlloc = nullptr;
+    DevLevel swz{}; uint8_t* swzAlloc = nullptr;
+    b2pbr_params params;
+    uint32_t* dRsqrt = nullptr;
+    float* dExpTab = nullptr;
+    Box* dBoxes = nullptr; int boxCap = 0;
+    Box* hBoxes = nullptr;           // pinned staging
+    cudaEvent_t boxCopied = nullptr;
+    std::vector<Box> lastBoxes;
+    uint64_t launches = 0;
+    bool profile = false;
+    std::vector<TraceEvent> trace;
+    float shadowW[11]; float shadowInvTotal;
+};
+
+static void pbrConstants(b2pbr* c) {
+    // PassObliqueShadowLight's compile-time tables (gui/dplug/gui/legacypbr.d:469-490): fallOff ^^ k and
+    // the normalisation, evaluated in double and narrowed once.
+    const float fallOff = 0.78f;
+    for (int s = 0; s < 11; ++s) c->shadowW[s] = (float)std::pow((double)fallOff, s);
+    const float total = (float)((1.0 - std::pow((double)fallOff, 11)) / (1.0 - (double)fallOff) - 1);
+    c->shadowInvTotal = (float)(1 / ((double)1.7f * (double)total));
+}
+
+static void normalized3(float x, float y, float z, float out[3]) {  // vec3f.normalized, math/dplug/math/vector.d:344-376
+    float s = 0;
+    s += x * x; s += y * y; s += z * z;
+    float inv = 1 / std::sqrt(s);
+    out[0] = x * inv; out[1] = y * inv; out[2] = z * inv;
+}
+
+static void pbrFreeMaps(b2pbr* c) {
+    b2mip_destroy(c->diffuse); b2mip_destroy(c->material); b2mip_destroy(c->depth);
+    c->diffuse = c->material = c->depth = nullptr;
+    if (c->outAlloc) cudaFree(c->outAlloc);
+    if (c->swzAlloc) cudaFree(c->swzAlloc);
+    c->outAlloc = c->swzAlloc = nullptr;
+}
+
+static void traceBegin(b2pbr* c, const char* name) {
+    if (!c->profile) return;
+    TraceEvent t; t.name = name;
+    cudaEventCreate(&t.beg); cudaEventCreate(&t.end);
+    cudaEventRecord(t.beg, c->stream);
+    c->trace.push_back(t);
+}
+static void traceEnd(b2pbr* c) {
+    if (!c->profile || c->trace.empty()) return;
+    cudaEventRecord(c->trace.back().end, c->stream);
+}
+
+static int pbrUploadBoxes(b2pbr* c, const b2_box2i* areas, int n) {
+    bool same = (int)c->lastBoxes.size() == n && n > 0 && memcmp(c->lastBoxes.data(), areas, sizeof(Box) * n) == 0;
+    if (same) return B2_OK;
+    if (n > c->boxCap) {
+        int cap = n < 4096 ? 4096 : n * 2;
+        if (c->dBoxes) { CU(cudaStreamSynchronize(c->stream)); cudaFree(c->dBoxes); cudaFreeHost(c->hBoxes); c->dBoxes = nullptr; c->hBoxes = nullptr; }
+        CU(cudaMalloc((void**)&c->dBoxes, sizeof(Box) * cap));
+        CU(cudaMallocHost((void**)&c->hBoxes, sizeof(Box) * cap));
+        c->boxCap = cap;
+    }
+    CU(cudaEventSynchronize(c->boxCopied));  // staging buffer free again?
+    memcpy(c->hBoxes, areas, sizeof(Box) * n);
+    CU(cudaMemcpyAsync(c->dBoxes, c->hBoxes, sizeof(Box) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->boxCopied, c->stream));
+    c->lastBoxes.assign((const Box*)areas, (const Box*)areas + n);
+    return B2_OK;
+}
+
+static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, b2mip* material, b2mip* depth) {
+    if (!c->outAlloc) return fail(B2_ERR_STATE, "compositeTile before resizeBuffers (compositor.d:41)");
+    if (!diffuse) diffuse = c->diffuse;
+    if (!material) material = c->material;
+    if (!depth) depth = c->depth;
+    if (diffuse->color != B2_COLOR_RGBA8 || material->color != B2_COLOR_RGBA8 || depth->color != B2_COLOR_L16)
+        return fail(B2_ERR_INVALID, "compositeTile: wrong map pixel types");
+    if (diffuse->W != c->W || diffuse->H != c->H || material->W != c->W || material->H != c->H || depth->W != c->W || depth->H != c->H)
+        return fail(B2_ERR_INVALID, "compositeTile: map size differs from resizeBuffers size");
+    if (n <= 0) return B2_OK;
+    for (int k = 0; k < n; ++k) {
+        const b2_box2i& a = areas[k];
+        if (!boxSorted(a) || a.min_x < 0 || a.min_y < 0 || a.max_x > c->W || a.max_y > c->H)
+            return fail(B2_ERR_INVALID, "compositeTile: area outside the frame");
+        if (a.min_y < c->out.y0 || a.max_y > c->out.y0 + c->out.rows)
+            if (!boxEmpty(a)) return fail(B2_ERR_INVALID, "compositeTile: area outside this band");
+    }
+    CU(cudaSetDevice(c->device));
+    int rc = pbrUploadBoxes(c, areas, n);
+    if (rc) return rc;
+    PbrArgs A;
+    memset(&A, 0, sizeof(A));
+    A.nDiffuse = (int)diffuse->levels.size();
+    A.nDepth = (int)depth->levels.size();
+    for (int l = 0; l < A.nDiffuse && l < kMaxDiffuseLevels; ++l) A.diffuse[l] = diffuse->levels[l];
+    for (int l = 0; l < A.nDepth && l < kMaxDepthLevels; ++l) A.depth[l] = depth->levels[l];
+    if (A.nDiffuse > kMaxDiffuseLevels) A.nDiffuse = kMaxDiffuseLevels;
+    if (A.nDepth > kMaxDepthLevels) A.nDepth = kMaxDepthLevels;
+    A.material = material->levels[0];
+    A.nSky = c->sky ? (int)c->sky->levels.size() : 0;
+    for (int l = 0; l < A.nSky; ++l) A.sky[l] = c->sky->levels[l];
+    A.out = c->out;
+    A.W = c->W; A.H = c->H;
+    A.boxes = c->dBoxes; A.nBoxes = n;
+    A.rsqrtTab = c->dRsqrt; A.expTab = c->dExpTab;
+    const b2pbr_params& p = c->params;
+    memcpy(A.light1, p.light1_color, 12); memcpy(A.light2Dir, p.light2_dir, 12); memcpy(A.light2Col, p.light2_color, 12);
+    memcpy(A.light3Dir, p.light3_dir, 12); memcpy(A.light3Col, p.light3_color, 12);
+    A.ambient = p.ambient_light; A.skyAmount = p.skybox_amount; A.toneThr = p.tonemap_threshold; A.toneRatio = p.tonemap_ratio;
+    A.passMask = p.pass_active_mask;
+    memcpy(A.shadowW, c->shadowW, sizeof(A.shadowW));
+    A.shadowInvTotal = c->shadowInvTotal;
+    A.invW = 1.0f / (float)c->W; A.invH = 1.0f / (float)c->H;
+    if (c->sky) {
+        A.skyPixels = (float)(c->sky->W * c->sky->H);
+        A.skyFX = (float)c->sky->W - 1.0f;
+        A.skyFY = (float)c->sky->H - 1.0f;
+    }
+    traceBegin(c, "PBR compositeTile");
+    launch_pbr_exact(A, n, c->stream);
+    c->launches++;
+    traceEnd(c);
+    CU(cudaGetLastError());
+    return B2_OK;
+}
+
+extern "C" {
+
+void b2pbr_default_params(b2pbr_params* p) {
+    if (!p) return;
+    for (int k = 0; k < 3; ++k) p->light1_color[k] = 0.25f * 1.3f;   // legacypbr.d:453
+    normalized3(0.0f, 1.0f, 0.1f, p->light2_dir);                    // legacypbr.d:626
+    for (int k = 0; k < 3; ++k) p->light2_color[k] = 0.481f;         // legacypbr.d:629
+    normalized3(0.0f, 1.0f, 0.1f, p->light3_dir);                    // legacypbr.d:676
+    for (int k = 0; k < 3; ++k) p->light3_color[k] = 0.26f;          // legacypbr.d:679
+    p->ambient_light = 0.08125f;                                     // legacypbr.d:391
+    p->skybox_amount = 0.52f;                                        // legacypbr.d:843
+    p->tonemap_threshold = 1.0f;                                     // legacypbr.d:1045
+    p->tonemap_ratio = 0.3f;                                         // legacypbr.d:1049
+    p->pass_active_mask = 0xffu;
+}
+
+static int pbrCreate(b2pbr** out, int device, bool banded, int y0, int y1) {
+    if (!out) return fail(B2_ERR_INVALID, "b2pbr_create: null out");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(B2_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)"); }
+    if (device < 0 || device >= ndev) return fail(B2_ERR_INVALID, "bad device index");
+    CU(cudaSetDevice(device));
+    b2pbr* c = new b2pbr();
+    c->device = device; c->banded = banded; c->bandY0 = y0; c->bandY1 = y1;
+    b2pbr_default_params(&c->params);
+    pbrConstants(c);
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->ownStream = true;
+    CU(cudaEventCreateWithFlags(&c->boxCopied, cudaEventDisableTiming));
+    CU(cudaMalloc((void**)&c->dRsqrt, sizeof(kRsqrtssTable)));
+    CU(cudaMemcpy(c->dRsqrt, kRsqrtssTable, sizeof(kRsqrtssTable), cudaMemcpyHostToDevice));
+    float expTab[256];
+    for (int r = 0; r < 256; ++r) {  // PassSpecularLight._exponentTable, legacypbr.d:696-702
+        float arg = (1 - r / 255.0f) * 5.5f;
+        float t = 0.8f * (float)std::exp((double)arg);
+        t *= 2.8f;
+        expTab[r] = t;
+    }
+    CU(cudaMalloc((void**)&c->dExpTab, sizeof(expTab)));
+    CU(cudaMemcpy(c->dExpTab, expTab, sizeof(expTab), cudaMemcpyHostToDevice));
+    *out = c;
+    return B2_OK;
+}
+int b2pbr_create(b2pbr** out, int device) { return pbrCreate(out, device, false, 0, 0); }
+int b2pbr_create_band(b2pbr** out, int device, int y0, int y1) {
+    if (y0 < 0 || y1 < y0) return fail(B2_ERR_INVALID, "b2pbr_create_band: bad rows");
+    return pbrCreate(out, device, true, y0, y1);
+}
+void b2pbr_destroy(b2pbr* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    pbrFreeMaps(c);
+    b2mip_destroy(c->sky);
+    if (c->dRsqrt) cudaFree(c->dRsqrt);
+    if (c->dExpTab) cudaFree(c->dExpTab);
+    if (c->dBoxes) cudaFree(c->dBoxes);
+    if (c->hBoxes) cudaFreeHost(c->hBoxes);
+    if (c->boxCopied) cudaEventDestroy(c->boxCopied);
+    for (auto& t : c->trace) { cudaEventDestroy(t.beg); cudaEventDestroy(t.end); }
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+int b2pbr_set_stream(b2pbr* c, void* s) {
+    if (!c) return fail(B2_ERR_INVALID, "null compositor");
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)s;
+    c->ownStream = false;
+    for (b2mip* m : {c->diffuse, c->material, c->depth, c->sky})
+        if (m) b2mip_set_stream(m, s);
+    return B2_OK;
+}
+
+int b2pbr_resize(b2pbr* c, int width, int height, int tw, int th) {
+    if (!c || width <= 0 || height <= 0 || tw <= 0 || th <= 0) return fail(B2_ERR_INVALID, "resizeBuffers: bad arguments");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    pbrFreeMaps(c);
+    c->lastBoxes.clear();
+    c->W = width; c->H = height; c->tileW = tw; c->tileH = th;
+    int y0 = 0, y1 = height, dUp = 0, dDown = 0, zUp = 0, zDown = 0;
+    if (c->banded) {
+        if (c->bandY1 > height) return fail(B2_ERR_INVALID, "resizeBuffers: band outside the canvas");
+        y0 = c->bandY0; y1 = c->bandY1;
+        // rows of level 0 a band needs beyond its own for the level-5 bicubic bloom
+        // (94) and the level-4 AO pyramid / 10-row shadow reach (28)
+        dUp = dDown = 96; zUp = zDown = 32;
+    }
+    int rc;
+    // GUIGraphics.doResize, graphics.d:1118-1128
+    if ((rc = mipCreate(&c->diffuse, c->device, B2_COLOR_RGBA8, 5, width, height, y0, y1, dUp, dDown))) return rc;
+    if ((rc = mipCreate(&c->depth, c->device, B2_COLOR_L16, 4, width, height, y0, y1, zUp, zDown))) return rc;
+    if ((rc = mipCreate(&c->material, c->device, B2_COLOR_RGBA8, 0, width, height, y0, y1, 0, 0))) return rc;
+    for (b2mip* m : {c->diffuse, c->material, c->depth}) {
+        cudaStreamSynchronize(m->stream);
+        b2mip_set_stream(m, c->stream);
+    }
+    // _compositedBuffer (graphics.d:1136)
+    c->out.w = width; c->out.h = height; c->out.pitch = (int)alignUp((size_t)width * 4, 128);
+    c->out.y0 = y0; c->out.rows = y1 - y0;
+    CU(cudaMalloc((void**)&c->outAlloc, (size_t)c->out.pitch * (size_t)(c->out.rows > 0 ? c->out.rows : 1)));
+    CU(cudaMemsetAsync(c->outAlloc, 0, (size_t)c->out.pitch * (size_t)(c->out.rows > 0 ? c->out.rows : 1), c->stream));
+    c->out.base = c->outAlloc;
+    c->swz = c->out;
+    CU(cudaMalloc((void**)&c->swzAlloc, (size_t)c->out.pitch * (size_t)(c->out.rows > 0 ? c->out.rows : 1)));
+    c->swz.base = c->swzAlloc;
+    return B2_OK;
+}
+
+int b2pbr_set_params(b2pbr* c, const b2pbr_params* p) {
+    if (!c || !p) return fail(B2_ERR_INVALID, "set_params: null");
+    c->params = *p;
+    return B2_OK;
+}
+int b2pbr_get_params(const b2pbr* c, b2pbr_params* p) {
+    if (!c || !p) return fail(B2_ERR_INVALID, "get_params: null");
+    *p = c->params;
+    return B2_OK;
+}
+
+int b2pbr_set_skybox(b2pbr* c, const uint8_t* rgba, int w, int h, size_t pitch) {
+    if (!c) return fail(B2_ERR_INVALID, "null compositor");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    b2mip_destroy(c->sky);
+    c->sky = nullptr;
+    if (!rgba) return B2_OK;
+    if (w <= 0 || h <= 0) return fail(B2_ERR_INVALID, "setSkybox: empty image");
+    int rc = b2mip_create(&c->sky, c->device, B2_COLOR_RGBA8, 12, w, h);  // legacypbr.d:868
+    if (rc) return rc;
+    cudaStreamSynchronize(c->sky->stream);
+    b2mip_set_stream(c->sky, c->stream);
+    b2_box2i whole{0, 0, w, h};
+    if ((rc = b2mip_upload(c->sky, 0, rgba, pitch, &whole, 1))) return rc;
+    CU(cudaStreamSynchronize(c->stream));  // the caller may free its image right after this call
+    if ((rc = b2mip_generate_mipmaps(c->sky, B2_QUALITY_BOX))) return rc;  // legacypbr.d:869
+    c->launches += c->sky->launches;
+    return B2_OK;
+}
+
+b2mip* b2pbr_map(b2pbr* c, int which) {
+    if (!c) return nullptr;
+    switch (which) {
+        case B2_MAP_DIFFUSE: return c->diffuse;
+        case B2_MAP_MATERIAL: return c->material;
+        case B2_MAP_DEPTH: return c->depth;
+    }
+    return nullptr;
+}
+b2mip* b2pbr_skybox(b2pbr* c) { return c ? c->sky : nullptr; }
+int b2pbr_output(b2pbr* c, b2_imageref* out) {
+    if (!c || !out || !c->outAlloc) return fail(B2_ERR_STATE, "b2pbr_output: no buffers");
+    out->w = c->out.w; out->h = c->out.h; out->pitch = (size_t)c->out.pitch; out->pixels = c->out.base;
+    return B2_OK;
+}
+
+int b2pbr_regenerate_mipmaps(b2pbr* c, const b2_box2i* rects, int n) {
+    if (!c || !c->diffuse) return fail(B2_ERR_STATE, "regenerateMipmaps before resize");
+    if (n <= 0) return B2_OK;  // graphics.d:1358-1360
+    std::vector<b2_box2i> s0(rects, rects + n), s1(rects, rects + n);
+    uint64_t before = c->diffuse->launches + c->depth->launches;
+    traceBegin(c, "diffuse mipmap");
+    for (int level = 1; level < (int)c->diffuse->levels.size(); ++level) {
+        int q = level == 1 ? B2_QUALITY_BOX_ALPHACOV_PREMUL : B2_QUALITY_CUBIC;  // graphics.d:1380-1384
+        for (auto& area : s0) {
+            int rc = b2mip_generate_next_level(c->diffuse, q, area, level, &area);
+            if (rc) return rc;
+        }
+    }
+    traceEnd(c);
+    // depth: replicateBordersTouching(area) (graphics.d:1406-1408) is clamp-to-edge addressing on the device
+    traceBegin(c, "depth mipmap");
+    for (int level = 1; level < (int)c->depth->levels.size(); ++level) {
+        int q = level >= 3 ? B2_QUALITY_CUBIC : B2_QUALITY_BOX;  // graphics.d:1414
+        for (auto& area : s1) {
+            int rc = b2mip_generate_next_level(c->depth, q, area, level, &area);
+            if (rc) return rc;
+        }
+    }
+    traceEnd(c);
+    c->launches += c->diffuse->launches + c->depth->launches - before;
+    return B2_OK;
+}
+
+int b2pbr_composite_tile(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, b2mip* material, b2mip* depth) {
+    if (!c || (n > 0 && !areas)) return fail(B2_ERR_INVALID, "compositeTile: bad arguments");
+    return pbrComposite(c, areas, n, diffuse, material, depth);
+}
+
+int b2pbr_composite_raw(b2pbr* c, const b2_box2i* areas, int n) {
+    if (!c || !c->outAlloc || (n > 0 && !areas)) return fail(B2_ERR_STATE, "composite_raw: bad state");
+    if (n <= 0) return B2_OK;
+    CU(cudaSetDevice(c->device));
+    int rc = pbrUploadBoxes(c, areas, n);
+    if (rc) return rc;
+    launch_copy_diffuse(c->out, c->diffuse->levels[0], c->dBoxes, n, n, c->stream);
+    c->launches++;
+    CU(cudaGetLastError());
+    return B2_OK;
+}
+
+int b2pbr_download(b2pbr* c, void* host, size_t host_pitch, const b2_box2i* rects, int n) {
+    if (!c || !c->outAlloc || !host) return fail(B2_ERR_STATE, "download: bad state");
+    CU(cudaSetDevice(c->device));
+    for (int k = 0; k < n; ++k) {
+        const b2_box2i& r = rects[k];
+        if (!boxSorted(r) || r.min_x < 0 || r.min_y < c->out.y0 || r.max_x > c->W || r.max_y > c->out.y0 + c->out.rows)
+            return fail(B2_ERR_INVALID, "download: rectangle outside the stored frame");
+        if (boxEmpty(r)) continue;
+        CU(cudaMemcpy2DAsync((uint8_t*)host + (size_t)r.min_y * host_pitch + (size_t)r.min_x * 4, host_pitch,
+                             c->out.base + (size_t)(r.min_y - c->out.y0) * c->out.pitch + (size_t)r.min_x * 4, (size_t)c->out.pitch,
+                             (size_t)boxW(r) * 4, (size_t)boxH(r), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
+int b2pbr_download_swizzled(b2pbr* c, int pf, void* host, size_t host_pitch, const b2_box2i* rects, int n) {
+    if (!c || !c->outAlloc || !host || pf < 0 || pf > 2) return fail(B2_ERR_STATE, "download_swizzled: bad arguments");
+    CU(cudaSetDevice(c->device));
+    for (int k = 0; k < n; ++k) {
+        const b2_box2i& r = rects[k];
+        if (!boxSorted(r) || r.min_x < 0 || r.min_y < c->out.y0 || r.max_x > c->W || r.max_y > c->out.y0 + c->out.rows)
+            return fail(B2_ERR_INVALID, "download_swizzled: rectangle outside the stored frame");
+        if (boxEmpty(r)) continue;
+        launch_swizzle(c->swz, c->out, toBox(r), pf, c->stream);
+        c->launches++;
+        CU(cudaMemcpy2DAsync((uint8_t*)host + (size_t)r.min_y * host_pitch + (size_t)r.min_x * 4, host_pitch,
+                             c->swz.base + (size_t)(r.min_y - c->swz.y0) * c->swz.pitch + (size_t)r.min_x * 4, (size_t)c->swz.pitch,
+                             (size_t)boxW(r) * 4, (size_t)boxH(r), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
+int b2pbr_composite_tile_host(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, int n_areas, const b2_box2i* update_rects,
+                              int n_update, b2_imageref diffuse_l0, b2_imageref material_l0, b2_imageref depth_l0) {
+    if (!c || !c->diffuse) return fail(B2_ERR_STATE, "compositeTile(host) before resizeBuffers");
+    if (diffuse_l0.w != c->W || diffuse_l0.h != c->H || material_l0.w != c->W || material_l0.h != c->H ||
+        depth_l0.w != c->W || depth_l0.h != c->H || wfb.w != c->W || wfb.h != c->H)
+        return fail(B2_ERR_INVALID, "compositeTile(host): image size differs from resizeBuffers size");
+    if (!update_rects) { update_rects = areas; n_update = n_areas; }
+    int rc;
+    traceBegin(c, "upload dirty rects");
+    if ((rc = b2mip_upload(c->diffuse, 0, diffuse_l0.pixels, diffuse_l0.pitch, update_rects, n_update))) return rc;
+    if ((rc = b2mip_upload(c->material, 0, material_l0.pixels, material_l0.pitch, update_rects, n_update))) return rc;
+    if ((rc = b2mip_upload(c->depth, 0, depth_l0.pixels, depth_l0.pitch, update_rects, n_update))) return rc;
+    traceEnd(c);
+    if ((rc = b2pbr_regenerate_mipmaps(c, update_rects, n_update))) return rc;
+    if ((rc = pbrComposite(c, areas, n_areas, nullptr, nullptr, nullptr))) return rc;
+    traceBegin(c, "download composited");
+    rc = b2pbr_download(c, wfb.pixels, wfb.pitch, areas, n_areas);
+    traceEnd(c);
+    return rc;
+}
+
+int b2pbr_sync(b2pbr* c) {
+    if (!c) return fail(B2_ERR_INVALID, "null compositor");
+    CU(cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
+int b2pbr_profile_enable(b2pbr* c, int on) {
+    if (!c) return fail(B2_ERR_INVALID, "null compositor");
+    c->profile = on != 0;
+    return B2_OK;
+}
+
+int b2pbr_trace_json(b2pbr* c, char* buf, size_t cap, size_t* needed) {
+    if (!c) return fail(B2_ERR_INVALID, "null compositor");
+    CU(cudaStreamSynchronize(c->stream));
+    // Chrome Trace Event Format, like TraceProfiler (core/dplug/core/profiler.d:177-207): timestamps in
+    // microseconds relative to the first recorded event.
+    std::string s = "[";
+    char line[256];
+    for (size_t i = 0; i < c->trace.size(); ++i) {
+        float t0 = 0, dt = 0;
+        cudaEventElapsedTime(&t0, c->trace[0].beg, c->trace[i].beg);
+        cudaEventElapsedTime(&dt, c->trace[i].beg, c->trace[i].end);
+        snprintf(line, sizeof(line), "%s{\"name\":\"%s\",\"cat\":\"gpu\",\"ph\":\"X\",\"ts\":%.3f,\"dur\":%.3f,\"pid\":0,\"tid\":%d}",
+                 i ? "," : "", c->trace[i].name.c_str(), t0 * 1000.0, dt * 1000.0, c->device);
+        s += line;
+    }
+    s += "]";
+    if (needed) *needed = s.size() + 1;
+    if (buf && cap > 0) {
+        size_t nb = s.size() + 1 < cap ? s.size() + 1 : cap;
+        memcpy(buf, s.c_str(), nb);
+        buf[nb - 1] = 0;
+    }
+    return B2_OK;
+}
+
+uint64_t b2pbr_kernel_launches(const b2pbr* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

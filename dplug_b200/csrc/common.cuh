@@ -1,0 +1,60 @@
+// Shared device/host structures of libb2pbr (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace b2 {
+
+// One level of a device-resident pyramid.  Coordinates handed to kernels are GLOBAL
+// (whole-canvas) level coordinates; `y0` is the global row stored at `base`, so a
+// row-band object simply has y0 != 0 and rows < h.  Pitch is a multiple of 128 B and
+// `base` is 256-B aligned, so absolute-x-aligned 128-bit accesses are legal.
+struct DevLevel {
+    uint8_t* base;
+    int pitch;  // bytes
+    int w, h;   // global level size
+    int y0;     // global row index of stored row 0
+    int rows;   // stored rows
+};
+
+template <typename T>
+__device__ __forceinline__ const T* rowPtr(const DevLevel& L, int y) {
+    return reinterpret_cast<const T*>(L.base + (size_t)(y - L.y0) * (size_t)L.pitch);
+}
+template <typename T>
+__device__ __forceinline__ T* rowPtrW(const DevLevel& L, int y) {
+    return reinterpret_cast<T*>(L.base + (size_t)(y - L.y0) * (size_t)L.pitch);
+}
+
+struct Box { int minx, miny, maxx, maxy; };
+
+constexpr int kMaxDiffuseLevels = 6;   // Mipmap(5): gui/dplug/gui/graphics.d:1118
+constexpr int kMaxDepthLevels = 5;     // Mipmap(4): graphics.d:1119
+constexpr int kMaxSkyLevels = 13;      // Mipmap(12): gui/dplug/gui/legacypbr.d:868
+
+// Everything the lighting kernel needs, passed by value (__grid_constant__).
+struct PbrArgs {
+    DevLevel diffuse[kMaxDiffuseLevels];
+    DevLevel depth[kMaxDepthLevels];
+    DevLevel material;
+    DevLevel sky[kMaxSkyLevels];
+    DevLevel out;
+    int nDiffuse, nDepth, nSky;
+    int W, H;                 // level-0 size (global)
+    const Box* boxes;         // work list
+    int nBoxes;
+    const uint32_t* rsqrtTab; // 2048 entries
+    const float* expTab;      // 256 entries, PassSpecularLight._exponentTable
+    // parameters
+    float light1[3], light2Dir[3], light2Col[3], light3Dir[3], light3Col[3];
+    float ambient, skyAmount, toneThr, toneRatio;
+    uint32_t passMask;
+    // precomputed constants (host side, see pbr_constants())
+    float shadowW[11];
+    float shadowInvTotal;
+    float invW, invH;
+    float skyPixels, skyFX, skyFY;
+};
+
+}  // namespace b2

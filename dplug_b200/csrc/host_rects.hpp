@@ -1,0 +1,95 @@
+// Host-side rectangle algebra of the compositor's tile scheduler: the product's own implementation of
+// box2i (math/dplug/math/box.d), Mipmap.impactOnNextLevel (graphics/dplug/graphics/mipmap.d:623-645),
+// tileAreas / removeOverlappingAreas (gui/dplug/gui/boxlist.d:54-167) and
+// convertPBRLayerRectToRawLayerRect (gui/dplug/gui/graphics.d:981-1002).
+#pragma once
+#include <vector>
+#include "../../include/b2pbr.h"
+
+namespace b2 {
+
+inline int boxW(const b2_box2i& b) { return b.max_x - b.min_x; }
+inline int boxH(const b2_box2i& b) { return b.max_y - b.min_y; }
+// box.d:188-192 — a box is empty as soon as one dimension is degenerate
+inline bool boxEmpty(const b2_box2i& b) { return b.min_x == b.max_x || b.min_y == b.max_y; }
+inline bool boxSorted(const b2_box2i& b) { return b.min_x <= b.max_x && b.min_y <= b.max_y; }
+inline bool boxContains(const b2_box2i& a, const b2_box2i& o) {
+    return !(o.min_x < a.min_x || o.max_x > a.max_x || o.min_y < a.min_y || o.max_y > a.max_y);
+}
+// box.d:298-319 — an empty operand is returned as is
+inline b2_box2i boxIntersect(const b2_box2i& a, const b2_box2i& o) {
+    if (boxEmpty(a)) return a;
+    if (boxEmpty(o)) return o;
+    b2_box2i r;
+    r.min_x = a.min_x > o.min_x ? a.min_x : o.min_x;
+    int hx = a.max_x < o.max_x ? a.max_x : o.max_x;
+    r.max_x = hx >= r.min_x ? hx : r.min_x;
+    r.min_y = a.min_y > o.min_y ? a.min_y : o.min_y;
+    int hy = a.max_y < o.max_y ? a.max_y : o.max_y;
+    r.max_y = hy >= r.min_y ? hy : r.min_y;
+    return r;
+}
+
+inline b2_box2i impactOnNextLevel(int quality, b2_box2i a, int curW, int curH) {
+    b2_box2i maxArea{0, 0, curW / 2, curH / 2};
+    b2_box2i n;
+    if (quality == B2_QUALITY_CUBIC) n = b2_box2i{(a.min_x - 1) / 2, (a.min_y - 1) / 2, (a.max_x + 2) / 2, (a.max_y + 2) / 2};
+    else n = b2_box2i{a.min_x / 2, a.min_y / 2, (a.max_x + 1) / 2, (a.max_y + 1) / 2};
+    return boxIntersect(n, maxArea);
+}
+
+inline void tileAreas(const b2_box2i* areas, int n, int maxW, int maxH, std::vector<b2_box2i>& out) {
+    for (int k = 0; k < n; ++k) {
+        const b2_box2i& a = areas[k];
+        const int w = boxW(a), h = boxH(a);
+        for (int y0 = 0; y0 < h; y0 += maxH)
+            for (int x0 = 0; x0 < w; x0 += maxW) {
+                int x1 = x0 + maxW < w ? x0 + maxW : w;
+                int y1 = y0 + maxH < h ? y0 + maxH : h;
+                out.push_back(b2_box2i{a.min_x + x0, a.min_y + y0, a.min_x + x1, a.min_y + y1});
+            }
+    }
+}
+
+inline void removeOverlappingAreas(std::vector<b2_box2i>& boxes, std::vector<b2_box2i>& filtered) {
+    for (size_t i = 0; i < boxes.size(); ++i) {
+        const b2_box2i A = boxes[i];
+        if (boxW(A) * boxH(A) <= 0) continue;
+        bool split = false;
+        for (size_t j = i + 1; j < boxes.size(); ++j) {
+            const b2_box2i B = boxes[j];
+            const b2_box2i C = boxIntersect(A, B);
+            if (!(boxSorted(C) && !boxEmpty(C))) continue;
+            if (boxContains(A, B)) {  // B adds nothing: drop it, keep scanning the element swapped in
+                boxes[j] = boxes.back();
+                boxes.pop_back();
+                --j;
+                continue;
+            }
+            split = true;
+            if (!boxContains(B, A)) {
+                const b2_box2i parts[4] = {{A.min_x, A.min_y, A.max_x, C.min_y}, {A.min_x, C.min_y, C.min_x, C.max_y},
+                                           {C.max_x, C.min_y, A.max_x, C.max_y}, {A.min_x, C.max_y, A.max_x, A.max_y}};
+                for (const b2_box2i& p : parts)
+                    if (!boxEmpty(p)) boxes.push_back(p);
+            }
+            break;
+        }
+        if (!split) filtered.push_back(A);
+    }
+}
+
+inline b2_box2i growRect(b2_box2i r, int margin, int width, int height) {
+    int xmin = r.min_x - margin, ymin = r.min_y - margin, xmax = r.max_x + margin, ymax = r.max_y + margin;
+    if (xmin < 0) xmin = 0;
+    if (ymin < 0) ymin = 0;
+    if (xmax > width) xmax = width;
+    if (ymax > height) ymax = height;
+    if (xmax < 0) xmax = 0;
+    if (ymax < 0) ymax = 0;
+    if (xmin > width) xmin = width;
+    if (ymin > height) ymin = height;
+    return b2_box2i{xmin, ymin, xmax, ymax};
+}
+
+}  // namespace b2

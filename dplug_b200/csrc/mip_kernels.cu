@@ -1,0 +1,313 @@
+// Mipmap down-sampling kernels (graphics/dplug/graphics/mipmap.d:676-1109), one launch per
+// generateLevel call.  All are HBM-bound streaming kernels: every thread reads whole aligned vectors from
+// two (box) or four (cubic) source rows and writes one vector of destination texels; warps cover
+// contiguous row segments.  Integer paths are bit-exact by construction; the alpha-premultiplying box
+// is float but uses only IEEE * and + (this file is compiled with -fmad=false).
+#include "common.cuh"
+
+namespace b2 {
+
+// ------------------------------------------------------------------------------------------------
+// SIMD-in-register helpers: an RGBA8 texel is split into two 16-bit lanes pairs (r,b) and (g,a) so four
+// channels are summed with two integer adds; sums up to 64*255 fit the 16-bit lanes.
+__device__ __forceinline__ uint32_t evenBytes(uint32_t v) { return v & 0x00ff00ffu; }
+__device__ __forceinline__ uint32_t oddBytes(uint32_t v) { return (v >> 8) & 0x00ff00ffu; }
+
+// generateLevelBoxRGBA — mipmap.d:676-762: (a+b+c+d+2)>>2 per channel
+__device__ __forceinline__ uint32_t box4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    uint32_t lo = evenBytes(a) + evenBytes(b) + evenBytes(c) + evenBytes(d) + 0x00020002u;
+    uint32_t hi = oddBytes(a) + oddBytes(b) + oddBytes(c) + oddBytes(d) + 0x00020002u;
+    return ((lo >> 2) & 0x00ff00ffu) | (((hi >> 2) & 0x00ff00ffu) << 8);
+}
+
+// generateLevelBoxAlphaCovIntoPremulRGBA — mipmap.d:861-896 (non-legacy branch)
+__device__ __forceinline__ void premulAccum(uint32_t p, float& r, float& g, float& b, float& a, bool first) {
+    const float inv = 1.0f / 255;
+    float fr = (float)(p & 0xff), fg = (float)((p >> 8) & 0xff), fb = (float)((p >> 16) & 0xff), fa = (float)(p >> 24);
+    float al = fa * inv;
+    float lr = fr * inv * fr * inv * al;
+    float lg = fg * inv * fg * inv * al;
+    float lb = fb * inv * fb * inv * al;
+    if (first) { r = lr; g = lg; b = lb; a = al; }
+    else { r = r + lr; g = g + lg; b = b + lb; a = a + al; }
+}
+__device__ __forceinline__ uint32_t premul4(uint32_t A, uint32_t B, uint32_t C, uint32_t D) {
+    float r, g, b, a;
+    premulAccum(A, r, g, b, a, true);
+    premulAccum(B, r, g, b, a, false);
+    premulAccum(C, r, g, b, a, false);
+    premulAccum(D, r, g, b, a, false);
+    uint32_t ur = (uint32_t)__float2int_rz(r * 0.25f * 255.0f + 0.5f) & 0xff;
+    uint32_t ug = (uint32_t)__float2int_rz(g * 0.25f * 255.0f + 0.5f) & 0xff;
+    uint32_t ub = (uint32_t)__float2int_rz(b * 0.25f * 255.0f + 0.5f) & 0xff;
+    uint32_t ua = (uint32_t)__float2int_rz(a * 0.25f * 255.0f + 0.5f) & 0xff;
+    return ur | (ug << 8) | (ub << 16) | (ua << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Box kernels.  Thread = 2 destination texels (x even) when the pair is inside the rectangle: one 128-bit
+// load per source row, one 64-bit store; ragged rectangle edges fall back to single texels.
+template <bool PREMUL>
+__global__ void __launch_bounds__(256) k_box_rgba(DevLevel dst, DevLevel src, Box r) {
+    const int xp = (r.minx >> 1) + blockIdx.x * blockDim.x + threadIdx.x;  // pair index in absolute coordinates
+    const int y = r.miny + blockIdx.y * blockDim.y + threadIdx.y;
+    if (y >= r.maxy) return;
+    const int x = xp * 2;
+    if (x >= r.maxx || x + 1 < r.minx) return;
+    const uint32_t* s0 = rowPtr<uint32_t>(src, 2 * y);
+    const uint32_t* s1 = rowPtr<uint32_t>(src, 2 * y + 1);
+    uint32_t* d = rowPtrW<uint32_t>(dst, y);
+    if (x >= r.minx && x + 1 < r.maxx) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(s0 + 2 * x));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(s1 + 2 * x));
+        uint2 o;
+        if (PREMUL) { o.x = premul4(a.x, a.y, b.x, b.y); o.y = premul4(a.z, a.w, b.z, b.w); }
+        else { o.x = box4(a.x, a.y, b.x, b.y); o.y = box4(a.z, a.w, b.z, b.w); }
+        *reinterpret_cast<uint2*>(d + x) = o;
+    } else {
+        for (int xx = max(x, r.minx); xx < min(x + 2, r.maxx); ++xx) {
+            const uint2 a = __ldg(reinterpret_cast<const uint2*>(s0 + 2 * xx));
+            const uint2 b = __ldg(reinterpret_cast<const uint2*>(s1 + 2 * xx));
+            d[xx] = PREMUL ? premul4(a.x, a.y, b.x, b.y) : box4(a.x, a.y, b.x, b.y);
+        }
+    }
+}
+
+// generateLevelBoxL16 — mipmap.d:764-794.  Thread = 4 destination texels: 128-bit load per source row
+// (8 x u16), 64-bit store.
+__device__ __forceinline__ uint32_t boxL16pair(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
+    uint32_t lo = ((a0 & 0xffffu) + (a0 >> 16) + (b0 & 0xffffu) + (b0 >> 16) + 2u) >> 2;
+    uint32_t hi = ((a1 & 0xffffu) + (a1 >> 16) + (b1 & 0xffffu) + (b1 >> 16) + 2u) >> 2;
+    return lo | (hi << 16);
+}
+__global__ void __launch_bounds__(256) k_box_l16(DevLevel dst, DevLevel src, Box r) {
+    const int xq = (r.minx >> 2) + blockIdx.x * blockDim.x + threadIdx.x;  // quad index, absolute
+    const int y = r.miny + blockIdx.y * blockDim.y + threadIdx.y;
+    if (y >= r.maxy) return;
+    const int x = xq * 4;
+    if (x >= r.maxx || x + 3 < r.minx) return;
+    const uint16_t* s0 = rowPtr<uint16_t>(src, 2 * y);
+    const uint16_t* s1 = rowPtr<uint16_t>(src, 2 * y + 1);
+    uint16_t* d = rowPtrW<uint16_t>(dst, y);
+    if (x >= r.minx && x + 3 < r.maxx) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(s0 + 2 * x));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(s1 + 2 * x));
+        uint2 o;
+        o.x = boxL16pair(a.x, a.y, b.x, b.y);
+        o.y = boxL16pair(a.z, a.w, b.z, b.w);
+        *reinterpret_cast<uint2*>(d + x) = o;
+    } else {
+        for (int xx = max(x, r.minx); xx < min(x + 4, r.maxx); ++xx) {
+            uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(s0 + 2 * xx));
+            uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(s1 + 2 * xx));
+            d[xx] = (uint16_t)(((a & 0xffffu) + (a >> 16) + (b & 0xffffu) + (b >> 16) + 2u) >> 2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cubic kernels — generateLevelCubicRGBA / L16, mipmap.d:902-1109: [1 3 3 1] x [1 3 3 1], (sum+32)>>6,
+// outer taps clamped to the image.  The filter is separable and integer, so summing rows first is exact.
+//
+// Thread = 2 destination texels (x even).  Source columns needed: 2x-1 .. 2x+4 (6 texels): the aligned
+// 128-bit vector 2x..2x+3 is loaded by the thread itself; column 2x-1 is the last texel of the left
+// neighbour lane's vector and column 2x+4 the first texel of the right neighbour's (warp shuffles); only
+// lanes on a warp / image edge issue an extra scalar load.
+__device__ __forceinline__ void vsumRGBA(uint32_t m1, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t& lo, uint32_t& hi) {
+    lo = evenBytes(m1) + 3u * evenBytes(p0) + 3u * evenBytes(p1) + evenBytes(p2);  // <= 8*255 per lane
+    hi = oddBytes(m1) + 3u * oddBytes(p0) + 3u * oddBytes(p1) + oddBytes(p2);
+}
+
+__global__ void __launch_bounds__(256) k_cubic_rgba(DevLevel dst, DevLevel src, Box r) {
+    const int xp = (r.minx >> 1) + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = r.miny + blockIdx.y * blockDim.y + threadIdx.y;  // uniform per warp (blockDim.x == 32)
+    if (y >= r.maxy) return;
+    const int x = xp * 2;
+    const int sw = src.w, sh = src.h;
+    const int ym = max(2 * y - 1, 0), yp = min(2 * y + 2, sh - 1);
+    const uint32_t* rm = rowPtr<uint32_t>(src, ym);
+    const uint32_t* r0 = rowPtr<uint32_t>(src, 2 * y);
+    const uint32_t* r1 = rowPtr<uint32_t>(src, 2 * y + 1);
+    const uint32_t* r2 = rowPtr<uint32_t>(src, yp);
+    // vertical pass on this lane's 4 aligned source columns 2x .. 2x+3 (clamped loads past the image edge)
+    uint32_t lo[6], hi[6];
+    const bool active = x < r.maxx && x + 1 >= r.minx && 2 * x < sw;
+    const bool vec = active && (2 * x + 3 < sw);
+    if (vec) {
+        uint4 a = __ldg(reinterpret_cast<const uint4*>(rm + 2 * x));
+        uint4 b = __ldg(reinterpret_cast<const uint4*>(r0 + 2 * x));
+        uint4 c = __ldg(reinterpret_cast<const uint4*>(r1 + 2 * x));
+        uint4 d = __ldg(reinterpret_cast<const uint4*>(r2 + 2 * x));
+        vsumRGBA(a.x, b.x, c.x, d.x, lo[1], hi[1]);
+        vsumRGBA(a.y, b.y, c.y, d.y, lo[2], hi[2]);
+        vsumRGBA(a.z, b.z, c.z, d.z, lo[3], hi[3]);
+        vsumRGBA(a.w, b.w, c.w, d.w, lo[4], hi[4]);
+    } else if (active) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int cx = min(2 * x + k, sw - 1);
+            vsumRGBA(__ldg(rm + cx), __ldg(r0 + cx), __ldg(r1 + cx), __ldg(r2 + cx), lo[1 + k], hi[1 + k]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 1; k <= 4; ++k) lo[k] = hi[k] = 0;
+    }
+    // neighbours: column 2x-1 = left lane's column index 4, column 2x+4 = right lane's column index 1
+    const unsigned full = 0xffffffffu;
+    uint32_t lLo = __shfl_up_sync(full, lo[4], 1), lHi = __shfl_up_sync(full, hi[4], 1);
+    uint32_t rLo = __shfl_down_sync(full, lo[1], 1), rHi = __shfl_down_sync(full, hi[1], 1);
+    const bool leftOk = __shfl_up_sync(full, (int)vec, 1) && threadIdx.x > 0;
+    const bool rightOk = __shfl_down_sync(full, (int)active, 1) && threadIdx.x < 31;
+    if (!active) return;
+    if (leftOk) { lo[0] = lLo; hi[0] = lHi; }
+    else {
+        int cx = max(2 * x - 1, 0);
+        vsumRGBA(__ldg(rm + cx), __ldg(r0 + cx), __ldg(r1 + cx), __ldg(r2 + cx), lo[0], hi[0]);
+    }
+    if (rightOk && 2 * x + 4 < sw) { lo[5] = rLo; hi[5] = rHi; }
+    else {
+        int cx = min(2 * x + 4, sw - 1);
+        vsumRGBA(__ldg(rm + cx), __ldg(r0 + cx), __ldg(r1 + cx), __ldg(r2 + cx), lo[5], hi[5]);
+    }
+    uint32_t* d = rowPtrW<uint32_t>(dst, y);
+    uint32_t o[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        // destination x+t: columns 2(x+t)-1 .. 2(x+t)+2 = local indices 2t .. 2t+3; the right-most tap is
+        // clamped to the last source column (mipmap.d:934-935)
+        uint32_t l3 = lo[2 * t + 3], h3 = hi[2 * t + 3];
+        if (2 * (x + t) + 2 > sw - 1) { l3 = lo[2 * t + 2]; h3 = hi[2 * t + 2]; }
+        uint32_t sl = lo[2 * t] + 3u * lo[2 * t + 1] + 3u * lo[2 * t + 2] + l3 + 0x00200020u;
+        uint32_t sh2 = hi[2 * t] + 3u * hi[2 * t + 1] + 3u * hi[2 * t + 2] + h3 + 0x00200020u;
+        o[t] = ((sl >> 6) & 0x00ff00ffu) | (((sh2 >> 6) & 0x00ff00ffu) << 8);
+    }
+    if (x >= r.minx && x + 1 < r.maxx) *reinterpret_cast<uint2*>(d + x) = make_uint2(o[0], o[1]);
+    else {
+        if (x >= r.minx && x < r.maxx) d[x] = o[0];
+        if (x + 1 >= r.minx && x + 1 < r.maxx) d[x + 1] = o[1];
+    }
+}
+
+// L16 variant: thread = 2 destination texels; vertical sums are 32-bit per column (<= 8*65535).
+__global__ void __launch_bounds__(256) k_cubic_l16(DevLevel dst, DevLevel src, Box r) {
+    const int xp = (r.minx >> 1) + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = r.miny + blockIdx.y * blockDim.y + threadIdx.y;
+    if (y >= r.maxy) return;
+    const int x = xp * 2;
+    const int sw = src.w, sh = src.h;
+    const int ym = max(2 * y - 1, 0), yp = min(2 * y + 2, sh - 1);
+    const uint16_t* rm = rowPtr<uint16_t>(src, ym);
+    const uint16_t* r0 = rowPtr<uint16_t>(src, 2 * y);
+    const uint16_t* r1 = rowPtr<uint16_t>(src, 2 * y + 1);
+    const uint16_t* r2 = rowPtr<uint16_t>(src, yp);
+    uint32_t v[6];
+    const bool active = x < r.maxx && x + 1 >= r.minx && 2 * x < sw;
+    const bool vec = active && (2 * x + 3 < sw);
+    if (vec) {
+        uint2 a = __ldg(reinterpret_cast<const uint2*>(rm + 2 * x));
+        uint2 b = __ldg(reinterpret_cast<const uint2*>(r0 + 2 * x));
+        uint2 c = __ldg(reinterpret_cast<const uint2*>(r1 + 2 * x));
+        uint2 d = __ldg(reinterpret_cast<const uint2*>(r2 + 2 * x));
+        v[1] = (a.x & 0xffffu) + 3u * (b.x & 0xffffu) + 3u * (c.x & 0xffffu) + (d.x & 0xffffu);
+        v[2] = (a.x >> 16) + 3u * (b.x >> 16) + 3u * (c.x >> 16) + (d.x >> 16);
+        v[3] = (a.y & 0xffffu) + 3u * (b.y & 0xffffu) + 3u * (c.y & 0xffffu) + (d.y & 0xffffu);
+        v[4] = (a.y >> 16) + 3u * (b.y >> 16) + 3u * (c.y >> 16) + (d.y >> 16);
+    } else if (active) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int cx = min(2 * x + k, sw - 1);
+            v[1 + k] = (uint32_t)__ldg(rm + cx) + 3u * __ldg(r0 + cx) + 3u * __ldg(r1 + cx) + __ldg(r2 + cx);
+        }
+    } else {
+#pragma unroll
+        for (int k = 1; k <= 4; ++k) v[k] = 0;
+    }
+    const unsigned full = 0xffffffffu;
+    uint32_t lv = __shfl_up_sync(full, v[4], 1), rv = __shfl_down_sync(full, v[1], 1);
+    const bool leftOk = __shfl_up_sync(full, (int)vec, 1) && threadIdx.x > 0;
+    const bool rightOk = __shfl_down_sync(full, (int)active, 1) && threadIdx.x < 31;
+    if (!active) return;
+    if (leftOk) v[0] = lv;
+    else {
+        int cx = max(2 * x - 1, 0);
+        v[0] = (uint32_t)__ldg(rm + cx) + 3u * __ldg(r0 + cx) + 3u * __ldg(r1 + cx) + __ldg(r2 + cx);
+    }
+    if (rightOk && 2 * x + 4 < sw) v[5] = rv;
+    else {
+        int cx = min(2 * x + 4, sw - 1);
+        v[5] = (uint32_t)__ldg(rm + cx) + 3u * __ldg(r0 + cx) + 3u * __ldg(r1 + cx) + __ldg(r2 + cx);
+    }
+    uint16_t* d = rowPtrW<uint16_t>(dst, y);
+    uint32_t o[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        uint32_t t3 = v[2 * t + 3];
+        if (2 * (x + t) + 2 > sw - 1) t3 = v[2 * t + 2];
+        o[t] = (v[2 * t] + 3u * v[2 * t + 1] + 3u * v[2 * t + 2] + t3 + 32u) >> 6;
+    }
+    if (x >= r.minx && x + 1 < r.maxx) *reinterpret_cast<uint32_t*>(d + x) = o[0] | (o[1] << 16);
+    else {
+        if (x >= r.minx && x < r.maxx) d[x] = (uint16_t)o[0];
+        if (x + 1 >= r.minx && x + 1 < r.maxx) d[x + 1] = (uint16_t)o[1];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SimpleRawCompositor — gui/dplug/gui/compositor.d:280-296: copy diffuse RGB, alpha = 255.
+__global__ void __launch_bounds__(256) k_copy_diffuse(DevLevel dst, DevLevel src, const Box* boxes, int nBoxes) {
+    for (int b = blockIdx.x; b < nBoxes; b += gridDim.x) {
+        const Box box = boxes[b];
+        for (int j = box.miny + threadIdx.y; j < box.maxy; j += blockDim.y)
+            for (int i = box.minx + threadIdx.x; i < box.maxx; i += blockDim.x)
+                rowPtrW<uint32_t>(dst, j)[i] = __ldg(rowPtr<uint32_t>(src, j) + i) | 0xff000000u;
+    }
+}
+
+// reorderComponents — gui/dplug/gui/graphics.d:1425-1452,1527-1654: RGBA -> RGBA/BGRA/ARGB, alpha = 255,
+// written to a staging image that is then copied to the host.
+__global__ void __launch_bounds__(256) k_swizzle(DevLevel dst, DevLevel src, Box box, int pf) {
+    const int i = box.minx + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = box.miny + blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= box.maxx || j >= box.maxy) return;
+    uint32_t p = __ldg(rowPtr<uint32_t>(src, j) + i);
+    uint32_t r = p & 0xff, g = (p >> 8) & 0xff, b = (p >> 16) & 0xff, o;
+    if (pf == 1) o = b | (g << 8) | (r << 16) | 0xff000000u;        // BGRA8
+    else if (pf == 2) o = 0xffu | (r << 8) | (g << 16) | (b << 24);  // ARGB8
+    else o = p | 0xff000000u;                                       // RGBA8
+    rowPtrW<uint32_t>(dst, j)[i] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+static inline dim3 gridFor(int nx, int ny, dim3 block) { return dim3((nx + block.x - 1) / block.x, (ny + block.y - 1) / block.y); }
+
+void launch_box_rgba(const DevLevel& dst, const DevLevel& src, Box r, bool premul, cudaStream_t s) {
+    dim3 block(32, 8);
+    int pairs = ((r.maxx + 1) >> 1) - (r.minx >> 1);
+    dim3 grid = gridFor(pairs, r.maxy - r.miny, block);
+    if (premul) k_box_rgba<true><<<grid, block, 0, s>>>(dst, src, r);
+    else k_box_rgba<false><<<grid, block, 0, s>>>(dst, src, r);
+}
+void launch_box_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s) {
+    dim3 block(32, 8);
+    int quads = ((r.maxx + 3) >> 2) - (r.minx >> 2);
+    k_box_l16<<<gridFor(quads, r.maxy - r.miny, block), block, 0, s>>>(dst, src, r);
+}
+void launch_cubic_rgba(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s) {
+    dim3 block(32, 8);
+    int pairs = ((r.maxx + 1) >> 1) - (r.minx >> 1);
+    k_cubic_rgba<<<gridFor(pairs, r.maxy - r.miny, block), block, 0, s>>>(dst, src, r);
+}
+void launch_cubic_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s) {
+    dim3 block(32, 8);
+    int pairs = ((r.maxx + 1) >> 1) - (r.minx >> 1);
+    k_cubic_l16<<<gridFor(pairs, r.maxy - r.miny, block), block, 0, s>>>(dst, src, r);
+}
+void launch_copy_diffuse(const DevLevel& dst, const DevLevel& src, const Box* boxes, int n, int grid, cudaStream_t s) {
+    k_copy_diffuse<<<grid, dim3(32, 8), 0, s>>>(dst, src, boxes, n);
+}
+void launch_swizzle(const DevLevel& dst, const DevLevel& src, Box box, int pf, cudaStream_t s) {
+    dim3 block(32, 8);
+    k_swizzle<<<gridFor(box.maxx - box.minx, box.maxy - box.miny, block), block, 0, s>>>(dst, src, box, pf);
+}
+
+}  // namespace b2

@@ -1,0 +1,197 @@
+/* b2pbr — C ABI of the B200-native (sm_100a) PBR compositor + mipmap pyramid.
+ *
+ * This is the drop-in boundary for ONE path of AuburnSounds/Dplug: the dplug:gui
+ * PBR compositor and the dplug:graphics Mipmap pyramid.  Every entry point names
+ * the reference interface it replaces (paths relative to the Dplug tree).  All
+ * arguments are plain pointers, sizes and PODs; no torch / C++ types.  The D-side
+ * binding a maintainer would add is shown in INTEGRATION.md and d/.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a B2_ERR_* code otherwise; the
+ *     reference's methods are `nothrow @nogc` and return void, so the D shim
+ *     asserts on non-zero.  b2_last_error() gives a message for the calling thread.
+ *   - there is NO CPU fallback: if no CUDA device is usable, create() fails.
+ *   - work is enqueued on the object's CUDA stream (b2*_set_stream, default: a
+ *     private non-blocking stream).  Functions that read results back to host
+ *     memory synchronise that stream; everything else is asynchronous.
+ *   - rectangles are half-open [min,max) in pixels, as box2i.
+ */
+#ifndef B2PBR_H
+#define B2PBR_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2PBR_ABI_VERSION 1
+
+/* box2i — math/dplug/math/box.d:29-30,51-55 ({min.x,min.y,max.x,max.y}, 4 x int32) */
+typedef struct { int min_x, min_y, max_x, max_y; } b2_box2i;
+/* ImageRef!T — graphics/dplug/graphics/image.d:127-131 (pitch in bytes) */
+typedef struct { int w, h; size_t pitch; void* pixels; } b2_imageref;
+
+enum { B2_OK = 0, B2_ERR_INVALID = 1, B2_ERR_CUDA = 2, B2_ERR_NO_DEVICE = 3, B2_ERR_STATE = 4, B2_ERR_NOMEM = 5 };
+
+/* pixel formats — graphics/dplug/graphics/color.d:307-321 (RGBA: r in the low byte) */
+enum { B2_COLOR_RGBA8 = 0, B2_COLOR_L16 = 1 };
+/* Mipmap!T.Quality — graphics/dplug/graphics/mipmap.d:36-46 (same order) */
+enum { B2_QUALITY_BOX = 0, B2_QUALITY_CUBIC = 1, B2_QUALITY_BOX_ALPHACOV_PREMUL = 2 };
+/* pass indices — gui/dplug/gui/legacypbr.d:129-139 */
+enum {
+    B2_PASS_NORMAL = 0, B2_PASS_AO = 1, B2_PASS_OBLIQUE_SHADOW = 2, B2_PASS_DIRECTIONAL = 3,
+    B2_PASS_SPECULAR = 4, B2_PASS_SKYBOX = 5, B2_PASS_EMISSIVE = 6, B2_PASS_CLAMP = 7
+};
+/* the maps GUIGraphics owns and lends to the compositor — gui/dplug/gui/graphics.d:117-122 */
+enum { B2_MAP_DIFFUSE = 0, B2_MAP_MATERIAL = 1, B2_MAP_DEPTH = 2 };
+/* window pixel orders for the fused post-composite swizzle — window/dplug/window/window.d WindowPixelFormat */
+enum { B2_PF_RGBA8 = 0, B2_PF_BGRA8 = 1, B2_PF_ARGB8 = 2 };
+
+const char* b2_last_error(void);
+int b2_abi_version(void);
+/* number of usable CUDA devices (0 if none) */
+int b2_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * b2mip — device-resident twin of Mipmap!RGBA / Mipmap!L16 (graphics/dplug/graphics/mipmap.d:30-646)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b2mip b2mip;
+
+/* Mipmap.this(maxLevel, w, h) + size() — mipmap.d:60-64, 80-126.  Level l is (w>>l) x (h>>l);
+ * the number of levels is min(maxLevel+1, halvings until a dimension is 0). */
+int b2mip_create(b2mip** out, int device, int color, int max_level, int w, int h);
+/* row-banded variant: the object stores only rows [y0 - halo_up, y1 + halo_down) of the
+ * global w x h level 0 (and the matching rows of every level); coordinates stay global. */
+int b2mip_create_band(b2mip** out, int device, int color, int max_level, int w, int h, int y0, int y1,
+                      int halo_up, int halo_down);
+/* ~this — mipmap.d:128-132 */
+void b2mip_destroy(b2mip*);
+int b2mip_set_stream(b2mip*, void* cuda_stream);
+/* numLevels / width / height — mipmap.d:499-514 */
+int b2mip_num_levels(const b2mip*);
+int b2mip_width(const b2mip*);
+int b2mip_height(const b2mip*);
+/* levels[level] as a *device* ImageRef (pixels = device address of the first stored row; for banded objects
+ * `first_row` receives the global row index that address corresponds to) */
+int b2mip_level(const b2mip*, int level, b2_imageref* out, int* first_row);
+/* host -> device copy of `n` rectangles of one level (host image addressed like ImageRef: `host` = pixel (0,0)) */
+int b2mip_upload(b2mip*, int level, const void* host, size_t host_pitch, const b2_box2i* rects, int n);
+/* device -> host, synchronises */
+int b2mip_download(b2mip*, int level, void* host, size_t host_pitch, const b2_box2i* rects, int n);
+/* Mipmap.generateNextLevel(quality, updateRectPreviousLevel, level) — mipmap.d:534-540; returns the updated
+ * rectangle of `level` (impactOnNextLevel, mipmap.d:623-645) in *out_rect */
+int b2mip_generate_next_level(b2mip*, int quality, b2_box2i update_rect_previous_level, int level, b2_box2i* out_rect);
+/* Mipmap.generateLevel(level, quality, updateRect) — mipmap.d:544-618 */
+int b2mip_generate_level(b2mip*, int level, int quality, b2_box2i update_rect);
+/* Mipmap.generateMipmaps(quality) — mipmap.d:517-528 (box silently becomes cubic from level 3) */
+int b2mip_generate_mipmaps(b2mip*, int quality);
+/* Whole pyramid from level 0 in fused launches (diffuse recipe: level 1 boxAlphaCovIntoPremul, levels >= 2
+ * cubic — gui/dplug/gui/graphics.d:1378-1392; depth recipe: levels 1,2 box, >= 3 cubic — graphics.d:1412-1419).
+ * Same results as the level-by-level chain over the full rectangle. */
+int b2mip_generate_chain(b2mip*, int first_quality, int cubic_from_level);
+/* the three samplers, evaluated on the device for `n` query points (test hook for mipmap.d:149-496) */
+int b2mip_sample(b2mip*, int kind /*0 linear,1 cubic,2 linearMipmap*/, int n, const float* level, const float* x,
+                 const float* y, float* out4);
+int b2mip_sync(b2mip*);
+
+/* rectangle propagation — Mipmap.impactOnNextLevel, mipmap.d:623-645 (host-side, no device work) */
+b2_box2i b2_impact_on_next_level(int quality, b2_box2i area, int current_level_w, int current_level_h);
+/* tileAreas — gui/dplug/gui/boxlist.d:139-167; returns the number of tiles (writes at most `cap`) */
+int b2_tile_areas(const b2_box2i* areas, int n, int max_w, int max_h, b2_box2i* out, int cap);
+/* removeOverlappingAreas — boxlist.d:54-118; may reorder `boxes`; returns the number of disjoint boxes */
+int b2_remove_overlapping_areas(b2_box2i* boxes, int n, b2_box2i* out, int cap);
+/* convertPBRLayerRectToRawLayerRect — gui/dplug/gui/graphics.d:981-1002 */
+b2_box2i b2_grow_rect(b2_box2i rect, int margin, int width, int height);
+
+/* ------------------------------------------------------------------------------------------
+ * b2pbr — device PBRCompositor : MultipassCompositor : ICompositor
+ *         (gui/dplug/gui/compositor.d:29-69,81-194; gui/dplug/gui/legacypbr.d:67-266)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b2pbr b2pbr;
+
+/* run-time settings of the 8 passes: the legacy setters (legacypbr.d:75-123), pass members
+ * (legacypbr.d:391,453,626-629,676-679,843,1045-1049) and CompositorPass.setActive (compositor.d:222-225) */
+typedef struct {
+    float light1_color[3];   /* PassObliqueShadowLight.color   */
+    float light2_dir[3];     /* PassDirectionalLight.direction */
+    float light2_color[3];   /* PassDirectionalLight.color     */
+    float light3_dir[3];     /* PassSpecularLight.direction    */
+    float light3_color[3];   /* PassSpecularLight.color        */
+    float ambient_light;     /* PassAmbientOcclusion.amount    */
+    float skybox_amount;     /* PassSkyboxReflections.amount   */
+    float tonemap_threshold; /* PassClampAndConvertTo8bit.tonemapThreshold */
+    float tonemap_ratio;     /* PassClampAndConvertTo8bit.tonemapRatio     */
+    uint32_t pass_active_mask; /* bit p = pass p active */
+} b2pbr_params;
+
+/* PBRCompositor defaults (legacypbr.d:391,453,626-629,676-679,843,1045-1049) */
+void b2pbr_default_params(b2pbr_params*);
+
+/* PBRCompositor.this(CompositorCreationContext*) — legacypbr.d:141-165.  The thread pool of the
+ * creation context has no device counterpart: tiles are scheduled over the GPU's SMs. */
+int b2pbr_create(b2pbr** out, int device);
+/* band variant: this object composites rows [y0,y1) of a global_w x global_h canvas; see b2mip_create_band */
+int b2pbr_create_band(b2pbr** out, int device, int y0, int y1);
+void b2pbr_destroy(b2pbr*);
+int b2pbr_set_stream(b2pbr*, void* cuda_stream);
+/* ICompositor.resizeBuffers(width, height, areaMaxWidth, areaMaxHeight) — compositor.d:43-46; legacypbr.d:180-198.
+ * Also (re)allocates the device twins GUIGraphics.doResize sizes next (graphics.d:1115-1137): diffuse
+ * Mipmap(5), depth Mipmap(4), material Mipmap(0) and the composited RGBA8 buffer. */
+int b2pbr_resize(b2pbr*, int width, int height, int area_max_width, int area_max_height);
+int b2pbr_set_params(b2pbr*, const b2pbr_params*);
+int b2pbr_get_params(const b2pbr*, b2pbr_params*);
+/* PassSkyboxReflections.setSkybox(OwnedImage!RGBA) — legacypbr.d:861-870: copies the host image to the
+ * device, builds Mipmap!RGBA(12, image) and generateMipmaps(Quality.box).  rgba == NULL removes the skybox.
+ * (The reference takes ownership of the image; here the caller keeps it.) */
+int b2pbr_set_skybox(b2pbr*, const uint8_t* rgba, int w, int h, size_t pitch);
+/* device twins owned by the compositor object */
+b2mip* b2pbr_map(b2pbr*, int which /* B2_MAP_* */);
+b2mip* b2pbr_skybox(b2pbr*);
+/* device ImageRef of the composited buffer (wfb twin, gapless RGBA8, r in the low byte) */
+int b2pbr_output(b2pbr*, b2_imageref* out);
+
+/* GUIGraphics.regenerateMipmaps() — gui/dplug/gui/graphics.d:1354-1423, for the given
+ * _rectsToUpdateDisjointedPBR: diffuse level 1 boxAlphaCovIntoPremul, levels 2..5 cubic; depth border
+ * (replicateBordersTouching == clamp-to-edge addressing on the device), depth levels 1,2 box, 3,4 cubic. */
+int b2pbr_regenerate_mipmaps(b2pbr*, const b2_box2i* rects, int n);
+
+/* ICompositor.compositeTile(wfb, areas, diffuseMap, materialMap, depthMap, profiler) —
+ * compositor.d:63-68, legacypbr.d:201-260 — on device-resident maps; writes the composited twin.
+ * `areas` are disjoint rectangles no larger than the area_max_* given to resize (gui tiles, boxlist.d:139-167).
+ * Passing NULL maps uses the compositor's own twins. */
+int b2pbr_composite_tile(b2pbr*, const b2_box2i* areas, int n, b2mip* diffuse, b2mip* material, b2mip* depth);
+
+/* Same call with HOST images, exactly the reference's arguments: uploads `areas` (grown by the sampling
+ * reach where needed: see DESIGN.md) of the three level-0 maps, regenerates the device mip levels the
+ * passes sample, composites, and copies `areas` of the result into wfb.  update_rects/n_update are
+ * GUIGraphics._rectsToUpdateDisjointedPBR (what changed in level 0); pass NULL/0 to treat `areas` as changed. */
+int b2pbr_composite_tile_host(b2pbr*, b2_imageref wfb, const b2_box2i* areas, int n_areas,
+                              const b2_box2i* update_rects, int n_update,
+                              b2_imageref diffuse_l0, b2_imageref material_l0, b2_imageref depth_l0);
+
+/* device -> host copy of rectangles of the composited buffer; synchronises */
+int b2pbr_download(b2pbr*, void* host, size_t host_pitch, const b2_box2i* rects, int n);
+/* fused post-composite step (graphics.d:1425-1452,1527-1654 reorderComponents): same download but
+ * swizzled to the window's pixel order with alpha forced to 255 */
+int b2pbr_download_swizzled(b2pbr*, int pixel_format, void* host, size_t host_pitch, const b2_box2i* rects, int n);
+int b2pbr_sync(b2pbr*);
+
+/* SimpleRawCompositor (compositor.d:260-298): copy diffuse RGB, alpha = 255, into the composited twin */
+int b2pbr_composite_raw(b2pbr*, const b2_box2i* areas, int n);
+
+/* IProfiler stand-in (core/dplug/core/profiler.d:29-64): when enabled, each stage is bracketed with CUDA
+ * events; b2pbr_trace_json writes Chrome Trace Event JSON like TraceProfiler (profiler.d:177-207). */
+int b2pbr_profile_enable(b2pbr*, int on);
+int b2pbr_trace_json(b2pbr*, char* buf, size_t cap, size_t* needed);
+/* number of kernels this object launched since creation (bench.py's gpu_launches) */
+uint64_t b2pbr_kernel_launches(const b2pbr*);
+uint64_t b2mip_kernel_launches(const b2mip*);
+
+/* pin / unpin caller memory so the host-image entry points copy at full PCIe rate */
+int b2_host_register(void* ptr, size_t bytes);
+int b2_host_unregister(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2PBR_H */

@@ -1,0 +1,206 @@
+"""GPU parity of the PBR compositor against the CPU oracle, through the C ABI.
+
+Tolerance (BASELINE.json north_star): +-1 LSB per 8-bit channel for the float lighting.  The exact-arithmetic
+kernel is expected to be bit-identical; the test records both."""
+import numpy as np
+import pytest
+from dplug_b200 import synth
+
+pytestmark = pytest.mark.gpu
+TOL_LSB = 1
+
+
+def _setup(b2, oracle, W, H, depth_kind="smooth", seed=synth.SEED, sky=True, params=None, threads=8):
+    d, m, z = synth.frame(W, H, seed, depth_kind)
+    comp = b2.PBRCompositor(0)
+    comp.resizeBuffers(W, H, 64, 64)
+    ref = oracle.Graphics(W, H, numThreads=threads)
+    if sky:
+        s = synth.skybox(256, 192, seed)
+        comp.setSkybox(s); ref.setSkybox(s)
+    if params is not None:
+        comp.set_params(params); ref.set_params(params)
+    comp.diffuseMap.upload(0, d); comp.materialMap.upload(0, m); comp.depthMap.upload(0, z)
+    ref.setInputs(d, m, z)
+    return comp, ref, (d, m, z)
+
+
+def _compare(got, exp, what=""):
+    diff = np.abs(got.astype(np.int16) - exp.astype(np.int16))
+    assert diff.max() <= TOL_LSB, "%s: max |diff| = %d LSB at %s" % (what, diff.max(), np.unravel_index(diff.argmax(), diff.shape))
+    return int(diff.max()), float((diff > 0).mean())
+
+
+@pytest.mark.parametrize("W,H,kind", [(620, 330, "smooth"), (620, 330, "noise"), (257, 131, "smooth"), (64, 64, "noise"), (33, 17, "smooth")])
+def test_full_frame_parity(b2, oracle, W, H, kind):
+    comp, ref, _ = _setup(b2, oracle, W, H, kind)
+    whole = [(0, 0, W, H)]
+    comp.regenerateMipmaps(whole)
+    comp.compositeGUI(whole)
+    got = comp.download()
+    exp = ref.fullFrame()
+    # the device mip levels feeding the passes are bit-exact
+    for level in range(1, 6):
+        if level < comp.diffuseMap.numLevels():
+            assert np.array_equal(comp.diffuseMap.download(level), ref.diffuseMap.download(level)), level
+    for level in range(1, 5):
+        if level < comp.depthMap.numLevels():
+            assert np.array_equal(comp.depthMap.download(level), ref.depthMap.download(level)), level
+    mx, frac = _compare(got, exp, "%dx%d %s" % (W, H, kind))
+    assert (got[..., 3] == 255).all()
+    assert mx == 0, "exact kernel expected bit-identical output, got max %d LSB on %.4f of channels" % (mx, frac)
+
+
+def test_distort_lighting_overrides(b2, oracle):
+    """examples/distort/source/gui.d:41-48 light set-up at its default 620x330 size (BASELINE config 1)."""
+    import ctypes as C
+    p = b2.default_params()
+    f = np.float32
+
+    def v3(x, y, z, s=1.0):
+        return (C.c_float * 3)(float(f(x) * f(s)), float(f(y) * f(s)), float(f(z) * f(s)))
+
+    def norm(x, y, z):
+        v = np.array([x, y, z], dtype=np.float32)
+        inv = f(1) / np.sqrt(f(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]))
+        return (C.c_float * 3)(*[float(c * inv) for c in v])
+
+    p.light1_color = v3(0.26, 0.24, 0.22, 0.98)
+    p.light2_dir = norm(-0.5, 1.0, 0.23)
+    p.light2_color = v3(0.36, 0.38, 0.40, 1.148)
+    p.light3_dir = norm(0.0, 1.0, 0.1)
+    p.light3_color = v3(0.2, 0.2, 0.2, 0.84)
+    p.ambient_light = 0.042
+    p.skybox_amount = 0.56
+    comp, ref, _ = _setup(b2, oracle, 620, 330, params=p)
+    whole = [(0, 0, 620, 330)]
+    comp.regenerateMipmaps(whole); comp.compositeGUI(whole)
+    _compare(comp.download(), ref.fullFrame(), "distort lights")
+
+
+@pytest.mark.parametrize("mask", [0xff & ~(1 << k) for k in range(7)] + [0x81, 0x83, 0x91, 0xa1, 0xc1])
+def test_pass_masks(b2, oracle, mask):
+    """CompositorPass.setActive (compositor.d:222-236): every single pass switched off, and single-pass set-ups.
+    (With the normal pass off the reference reads stale scratch; only masks that keep it on or use no normal
+    consumer are compared.)"""
+    if not (mask & 1) and (mask & 0x38):
+        mask &= ~0x38  # passes that consume the normal buffer are undefined without PassComputeNormal
+    p = b2.default_params()
+    p.pass_active_mask = mask
+    W, H = 200, 120
+    comp, ref, _ = _setup(b2, oracle, W, H, params=p)
+    whole = [(0, 0, W, H)]
+    comp.regenerateMipmaps(whole); comp.compositeGUI(whole)
+    _compare(comp.download(), ref.fullFrame(), "mask %02x" % mask)
+
+
+def test_no_skybox(b2, oracle):
+    comp, ref, _ = _setup(b2, oracle, 150, 90, sky=False)
+    whole = [(0, 0, 150, 90)]
+    comp.regenerateMipmaps(whole); comp.compositeGUI(whole)
+    _compare(comp.download(), ref.fullFrame(), "no skybox")
+
+
+def test_dirty_rect_update(b2, oracle):
+    """One frame fully composited, then a widget-sized change: dirty rect -> regenerateMipmaps(rect) ->
+    compositeGUI(rect grown by the update margin) on both back ends (graphics.d:884-1002,1338-1423).
+    Pixels outside the composited tiles must be untouched."""
+    W, H = 620, 330
+    comp, ref, (d, m, z) = _setup(b2, oracle, W, H)
+    whole = [(0, 0, W, H)]
+    comp.regenerateMipmaps(whole); comp.compositeGUI(whole)
+    exp0 = ref.fullFrame()
+    rng = np.random.default_rng(3)
+    for it in range(6):
+        x0, y0 = int(rng.integers(0, W - 40)), int(rng.integers(0, H - 40))
+        r = (x0, y0, x0 + int(rng.integers(8, 120)), y0 + int(rng.integers(8, 90)))
+        r = (r[0], r[1], min(r[2], W), min(r[3], H))
+        d2, m2, z2 = synth.frame(W, H, synth.SEED + 1 + it)
+        ys, xs = slice(r[1], r[3]), slice(r[0], r[2])
+        d[ys, xs] = d2[ys, xs]; m[ys, xs] = m2[ys, xs]; z[ys, xs] = z2[ys, xs]
+        comp.diffuseMap.upload(0, d, [r]); comp.materialMap.upload(0, m, [r]); comp.depthMap.upload(0, z, [r])
+        ref.setInputs(d, m, z)
+        comp.regenerateMipmaps([r]); ref.regenerateMipmaps([r])
+        grown = [b2.growRect(r, 20, W, H)]
+        comp.compositeGUI(grown); ref.compositeGUI(grown)
+        got, exp = comp.download(), np.array(ref.output())
+        _compare(got, exp, "dirty rect %s" % (r,))
+
+
+def test_host_drop_in_call(b2, oracle):
+    """ICompositor.compositeTile with HOST images (the e2e path): upload, device mips, composite, copy back."""
+    W, H = 300, 200
+    d, m, z = synth.frame(W, H)
+    comp = b2.PBRCompositor(0)
+    comp.resizeBuffers(W, H, 64, 64)
+    s = synth.skybox(128, 96)
+    comp.setSkybox(s)
+    ref = oracle.Graphics(W, H, numThreads=8)
+    ref.setSkybox(s); ref.setInputs(d, m, z)
+    wfb = np.zeros((H, W, 4), dtype=np.uint8)
+    tiles = b2.tileAreas([(0, 0, W, H)], 64, 64)
+    comp.compositeTile(wfb, tiles, d, m, z)
+    _compare(wfb, ref.fullFrame(), "host drop-in")
+    # partial update through the same call
+    r = (40, 50, 140, 120)
+    d2, m2, z2 = synth.frame(W, H, synth.SEED + 9)
+    ys, xs = slice(r[1], r[3]), slice(r[0], r[2])
+    d[ys, xs] = d2[ys, xs]; m[ys, xs] = m2[ys, xs]; z[ys, xs] = z2[ys, xs]
+    ref.setInputs(d, m, z); ref.regenerateMipmaps([r])
+    grown = [b2.growRect(r, 20, W, H)]
+    ref.compositeGUI(grown)
+    comp.compositeTile(wfb, b2.tileAreas(grown, 64, 64), d, m, z, updateRects=[r])
+    _compare(wfb, np.array(ref.output()), "host drop-in partial")
+
+
+def test_raw_compositor_and_swizzle(b2):
+    """SimpleRawCompositor (compositor.d:280-296) and reorderComponents (graphics.d:1425-1452)."""
+    W, H = 100, 60
+    d, m, z = synth.frame(W, H)
+    comp = b2.PBRCompositor(0)
+    comp.resizeBuffers(W, H)
+    comp.diffuseMap.upload(0, d)
+    comp.compositeRaw(b2.tileAreas([(0, 0, W, H)], 64, 64))
+    out = comp.download()
+    assert np.array_equal(out[..., :3], d[..., :3]) and (out[..., 3] == 255).all()
+    bgra = comp.download(pixelFormat=1)
+    assert np.array_equal(bgra[..., 0], d[..., 2]) and np.array_equal(bgra[..., 2], d[..., 0]) and (bgra[..., 3] == 255).all()
+    argb = comp.download(pixelFormat=2)
+    assert (argb[..., 0] == 255).all() and np.array_equal(argb[..., 1], d[..., 0]) and np.array_equal(argb[..., 3], d[..., 2])
+
+
+def test_4k_frame_properties_and_sampled_parity(b2, oracle):
+    """BASELINE config 2 (3840x2160, full re-composite).  The oracle is run on a band of tiles only (seconds),
+    the rest is covered by size-independent properties: alpha = 255 everywhere, tile-decomposition
+    independence (64x64 tiles vs one 3840x2160 area list vs 17x13 tiles give identical bytes)."""
+    W, H = 3840, 2160
+    comp, ref, _ = _setup(b2, oracle, W, H)
+    whole = [(0, 0, W, H)]
+    comp.regenerateMipmaps(whole)
+    comp.compositeGUI(whole)
+    got = comp.download()
+    assert (got[..., 3] == 255).all()
+    comp.compositeTile(None, b2.tileAreas(whole, 17, 13))
+    assert np.array_equal(comp.download(), got)
+    # oracle on three horizontal bands of tiles (top edge, middle, bottom edge)
+    ref.regenerateMipmaps(whole)
+    for band in [(0, 0, W, 64), (0, 1024, W, 1088), (0, H - 48, W, H)]:
+        ref.compositeGUI([band])
+        exp = np.array(ref.output())[band[1]:band[3]]
+        _compare(got[band[1]:band[3]], exp, "4K band %s" % (band,))
+
+
+def test_profiler_trace(b2):
+    """IProfiler stand-in: Chrome Trace Event JSON with one complete event per stage (profiler.d:177-207)."""
+    import json
+    W, H = 128, 128
+    d, m, z = synth.frame(W, H)
+    comp = b2.PBRCompositor(0)
+    comp.resizeBuffers(W, H)
+    comp.profileEnable(True)
+    wfb = np.zeros((H, W, 4), dtype=np.uint8)
+    comp.compositeTile(wfb, b2.tileAreas([(0, 0, W, H)], 64, 64), d, m, z)
+    ev = json.loads(comp.traceJSON())
+    names = [e["name"] for e in ev]
+    assert "PBR compositeTile" in names and "diffuse mipmap" in names and all(e["ph"] == "X" and e["dur"] >= 0 for e in ev)
+    assert comp.kernelLaunches() >= 10

@@ -1,0 +1,124 @@
+"""CPU-only checks of the product library: it loads, exports every symbol include/b2pbr.h declares, fails
+loudly without a GPU (no CPU fallback), and its host-side tile scheduler (rectangle algebra) matches the
+reference's known answers and the oracle."""
+import ctypes as C
+import os
+import re
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b2pbr.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2(?:pbr|mip)?_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(b2):
+    from dplug_b200 import _lib
+    l = C.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(l, n)]
+    assert not missing, missing
+    # and the Python binding table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == names
+    assert _lib.lib().b2_abi_version() == 1
+
+
+def test_no_cpu_fallback(b2):
+    """Without a CUDA device creation must fail with B2_ERR_NO_DEVICE — never silently compute on the CPU."""
+    from dplug_b200 import _lib
+    l = _lib.lib()
+    if l.b2_device_count() > 0:
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    assert l.b2pbr_create(C.byref(h), 0) == 3
+    assert b"no CUDA device" in l.b2_last_error()
+    assert l.b2mip_create(C.byref(h), 0, 0, 4, 64, 64) == 3
+    with pytest.raises(b2.B2Error):
+        b2.PBRCompositor(0)
+    with pytest.raises(b2.B2Error):
+        b2.Mipmap(b2.RGBA8, 4, 64, 64)
+
+
+def test_product_does_not_link_oracle():
+    """The shipped library and package must not reference oracle/ (parity claims depend on it)."""
+    pkg = os.path.join(ROOT, "dplug_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "b2ref" not in text and "oracle/" not in text.replace("oracle/rsqrtss_table.inc", ""), (dirpath, f)
+
+
+def test_remove_overlapping_areas_known_answer(b2):
+    # gui/dplug/gui/boxlist.d:120-135
+    assert b2.removeOverlappingAreas([(0, 0, 4, 4), (2, 2, 6, 6), (1, 1, 2, 2)]) == [(2, 2, 6, 6), (0, 0, 4, 2), (0, 2, 2, 4)]
+
+
+def test_tile_areas(b2, oracle):
+    assert len(b2.tileAreas([(0, 0, 3840, 2160)], 64, 64)) == 2040
+    t = b2.tileAreas([(0, 0, 620, 330)], 64, 64)
+    assert len(t) == 60 and t[0] == (0, 0, 64, 64) and t[9] == (576, 0, 620, 64) and t[59] == (576, 320, 620, 330)
+    rng = np.random.default_rng(11)
+    for _ in range(50):
+        rects = []
+        for _ in range(int(rng.integers(1, 5))):
+            x0, y0 = int(rng.integers(0, 500)), int(rng.integers(0, 300))
+            rects.append((x0, y0, x0 + int(rng.integers(1, 300)), y0 + int(rng.integers(1, 200))))
+        mw, mh = int(rng.integers(1, 100)), int(rng.integers(1, 100))
+        out = (oracle.box2i * 100000)()
+        n = oracle.lib().b2ref_tile_areas(oracle.boxes(rects), len(rects), mw, mh, out, 100000)
+        assert b2.tileAreas(rects, mw, mh) == [out[i].astuple() for i in range(n)]
+
+
+def test_remove_overlapping_random_vs_oracle(b2, oracle):
+    rng = np.random.default_rng(12)
+    for _ in range(200):
+        rects = []
+        for _ in range(int(rng.integers(1, 9))):
+            x0, y0 = int(rng.integers(0, 40)), int(rng.integers(0, 40))
+            rects.append((x0, y0, x0 + int(rng.integers(0, 30)), y0 + int(rng.integers(0, 30))))
+        out = (oracle.box2i * 4096)()
+        n = oracle.lib().b2ref_remove_overlapping_areas(oracle.boxes(rects), len(rects), out, 4096)
+        exp = [out[i].astuple() for i in range(n)]
+        got = b2.removeOverlappingAreas(rects)
+        assert got == exp
+        # property: disjoint, same coverage
+        cover = np.zeros((80, 80), dtype=np.int32)
+        for (a, b, c, d) in got:
+            cover[b:d, a:c] += 1
+        assert cover.max() <= 1
+        want = np.zeros((80, 80), dtype=bool)
+        for (a, b, c, d) in rects:
+            want[b:d, a:c] = True
+        assert np.array_equal(cover.astype(bool), want)
+
+
+def test_impact_on_next_level_vs_oracle(b2, oracle):
+    rng = np.random.default_rng(13)
+    for _ in range(500):
+        w, h = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+        x0, y0 = int(rng.integers(0, w)), int(rng.integers(0, h))
+        r = (x0, y0, int(rng.integers(x0, w + 1)), int(rng.integers(y0, h + 1)))
+        for q in (0, 1, 2):
+            assert b2.impactOnNextLevel(q, r, w, h) == oracle.lib().b2ref_impact_on_next_level(q, oracle.box2i(*r), w, h).astuple()
+
+
+def test_grow_rect(b2):
+    # gui/dplug/gui/graphics.d:981-1002 with the default 20-px update margin (graphics.d:719)
+    assert b2.growRect((100, 100, 150, 130), 20, 620, 330) == (80, 80, 170, 150)
+    assert b2.growRect((5, 5, 615, 325), 20, 620, 330) == (0, 0, 620, 330)
+    assert b2.growRect((-100, -100, -50, -50), 20, 620, 330) == (0, 0, 0, 0)
+
+
+def test_default_params_match_reference_defaults(b2, oracle):
+    p, q = b2.default_params(), oracle.default_params()
+    assert bytes(p) == bytes(q)
+    assert abs(p.light1_color[0] - 0.325) < 1e-6 and p.pass_active_mask == 0xff
+    assert abs(p.light2_dir[1] - 0.99503719) < 1e-6
