@@ -132,9 +132,11 @@ static int mipCheckRect(const b2mip* m, int level, const b2_box2i& r, const char
 
 static int mipGenerateLevel(b2mip* m, int level, int quality, b2_box2i r) {
     if (level < 1 || level >= (int)m->levels.size()) return fail(B2_ERR_INVALID, "generateLevel: level out of range");
+    // a degenerate rectangle makes every reference loop a no-op (mipmap.d:683,771,830,906,1046); Box.intersection
+    // hands such boxes back un-clipped (box.d:303-308), so they may even lie outside the level
+    if (boxW(r) <= 0 || boxH(r) <= 0) return B2_OK;
     int rc = mipCheckRect(m, level, r, "generateLevel");
     if (rc) return rc;
-    if (boxEmpty(r)) return B2_OK;
     const DevLevel& dst = m->levels[level];
     const DevLevel& src = m->levels[level - 1];
     // the source rows a destination row needs must be stored too (only relevant for row bands)
