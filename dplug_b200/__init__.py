@@ -4,7 +4,7 @@ Host-side mirror (Python, for tests and benchmarks) of the reference interface f
 `Mipmap`, `PBRCompositor`, `tileAreas` ... all backed by the CUDA library libb2pbr.so through its C ABI
 (include/b2pbr.h).  There is no CPU implementation in this package.
 """
-from ._lib import B2Error, LIB_PATH, box2i  # noqa: F401
+from ._lib import B2Error, LIB_PATH, box2i, BoxArray  # noqa: F401
 from .mipmap import Mipmap, Quality, RGBA8, L16  # noqa: F401
 from .compositor import PBRCompositor, default_params  # noqa: F401
 from .boxlist import tileAreas, removeOverlappingAreas, impactOnNextLevel, growRect  # noqa: F401

@@ -68,6 +68,7 @@ SIGNATURES = {
     "b2pbr_resize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "b2pbr_set_params": (C.c_int, [C.c_void_p, C.POINTER(params)]),
     "b2pbr_get_params": (C.c_int, [C.c_void_p, C.POINTER(params)]),
+    "b2pbr_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "b2pbr_set_skybox": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t]),
     "b2pbr_map": (C.c_void_p, [C.c_void_p, C.c_int]),
     "b2pbr_skybox": (C.c_void_p, [C.c_void_p]),
@@ -111,8 +112,25 @@ def check(rc):
         raise B2Error("b2pbr error %d: %s" % (rc, lib().b2_last_error().decode()))
 
 
+class BoxArray:
+    """A rectangle list already marshalled for the C ABI (reuse it across frames: tile lists are long)."""
+
+    def __init__(self, rects):
+        self.n = len(rects)
+        self.arr = boxes(rects)
+        self.rects = list(rects)
+
+    def __len__(self):
+        return self.n
+
+    def __iter__(self):
+        return iter(self.rects)
+
+
 def boxes(rects):
     """list of (minx,miny,maxx,maxy) -> ctypes array of box2i"""
+    if isinstance(rects, BoxArray):
+        return rects.arr
     arr = (box2i * max(1, len(rects)))()
     for i, r in enumerate(rects):
         arr[i] = r if isinstance(r, box2i) else box2i(*[int(v) for v in r])

@@ -20,6 +20,7 @@ UNITS = [
     ("b2pbr.cu", ["-fmad=false"]),
     ("mip_kernels.cu", ["-fmad=false"]),
     ("pbr_exact.cu", ["-fmad=false"]),
+    ("pbr_fast.cu", []),
 ]
 
 

@@ -10,6 +10,7 @@ PBR_TILE_MAX_HEIGHT = 64  # gui/dplug/gui/graphics.d:60
 
 DIFFUSE, MATERIAL, DEPTH = 0, 1, 2
 PF_RGBA8, PF_BGRA8, PF_ARGB8 = 0, 1, 2
+MODE_FAST, MODE_EXACT = 0, 1
 
 
 def default_params():
@@ -107,6 +108,10 @@ class PBRCompositor:
     def ambientLight(self, a): self._set("ambient_light", float(a))
     def tonemapThreshold(self, v): self._set("tonemap_threshold", float(v))
     def tonemapRatio(self, v): self._set("tonemap_ratio", float(v))
+
+    def setMode(self, mode):
+        """MODE_FAST (default): throughput kernel, +-1 LSB; MODE_EXACT: reference operation order, bit-identical."""
+        _lib.check(self._l.b2pbr_set_mode(self._h, int(mode)))
 
     def setPassActive(self, index, active):
         """getPass(index).setActive(active) — compositor.d:170-173,222-225."""

@@ -24,6 +24,8 @@ void launch_cubic_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStrea
 void launch_copy_diffuse(const DevLevel& dst, const DevLevel& src, const Box* boxes, int n, int grid, cudaStream_t s);
 void launch_swizzle(const DevLevel& dst, const DevLevel& src, Box box, int pf, cudaStream_t s);
 void launch_pbr_exact(const PbrArgs& args, int gridBlocks, cudaStream_t stream);
+void launch_pbr_fast(const PbrArgs& args, cudaStream_t stream);
+int pbr_fast_strip_rows();
 void launch_sample(const DevLevel* levels, int nLevels, int color, int kind, int n, const float* lvl, const float* x,
                    const float* y, float* out4, cudaStream_t stream);
 }  // namespace b2
@@ -211,9 +213,11 @@ int b2mip_upload(b2mip* m, int level, const void* host, size_t host_pitch, const
     for (int k = 0; k < n; ++k) {
         int rc = mipCheckRect(m, level, rects[k], "b2mip_upload");
         if (rc) return rc;
-        if (boxEmpty(rects[k])) continue;
+    }
+    std::vector<b2_box2i> merged;
+    mergeRects(rects, n, merged);
+    for (const b2_box2i& r : merged) {
         const DevLevel& L = m->levels[level];
-        const b2_box2i& r = rects[k];
         CU(cudaMemcpy2DAsync(L.base + (size_t)(r.min_y - L.y0) * L.pitch + (size_t)r.min_x * m->elem, (size_t)L.pitch,
                              (const uint8_t*)host + (size_t)r.min_y * host_pitch + (size_t)r.min_x * m->elem, host_pitch,
                              (size_t)boxW(r) * m->elem, (size_t)boxH(r), cudaMemcpyHostToDevice, m->stream));
@@ -226,9 +230,11 @@ int b2mip_download(b2mip* m, int level, void* host, size_t host_pitch, const b2_
     for (int k = 0; k < n; ++k) {
         int rc = mipCheckRect(m, level, rects[k], "b2mip_download");
         if (rc) return rc;
-        if (boxEmpty(rects[k])) continue;
+    }
+    std::vector<b2_box2i> merged;
+    mergeRects(rects, n, merged);
+    for (const b2_box2i& r : merged) {
         const DevLevel& L = m->levels[level];
-        const b2_box2i& r = rects[k];
         CU(cudaMemcpy2DAsync((uint8_t*)host + (size_t)r.min_y * host_pitch + (size_t)r.min_x * m->elem, host_pitch,
                              L.base + (size_t)(r.min_y - L.y0) * L.pitch + (size_t)r.min_x * m->elem, (size_t)L.pitch,
                              (size_t)boxW(r) * m->elem, (size_t)boxH(r), cudaMemcpyDeviceToHost, m->stream));
@@ -345,6 +351,9 @@ struct b2pbr {
     Box* hBoxes = nullptr;           // pinned staging
     cudaEvent_t boxCopied = nullptr;
     std::vector<Box> lastBoxes;
+    int lastBoxKind = -1;            // what dBoxes holds: 0 = the caller's areas, 1 = 32-column strips of them
+    int nDeviceBoxes = 0;
+    int mode = B2_MODE_FAST;
     uint64_t launches = 0;
     bool profile = false;
     std::vector<TraceEvent> trace;
@@ -387,21 +396,40 @@ static void traceEnd(b2pbr* c) {
     cudaEventRecord(c->trace.back().end, c->stream);
 }
 
-static int pbrUploadBoxes(b2pbr* c, const b2_box2i* areas, int n) {
-    bool same = (int)c->lastBoxes.size() == n && n > 0 && memcmp(c->lastBoxes.data(), areas, sizeof(Box) * n) == 0;
+// Uploads the work list of a launch.  kind 0: the caller's areas as they are (one CTA each); kind 1: the areas cut
+// into warp-sized strips of 32 columns x strip_rows rows for k_pbr_fast.  The list is kept on the device and
+// re-used while the caller passes the same areas (a full-frame tile list never changes between frames).
+static int pbrUploadBoxes(b2pbr* c, const b2_box2i* areas, int n, int kind) {
+    bool same = c->lastBoxKind == kind && (int)c->lastBoxes.size() == n && n > 0 && memcmp(c->lastBoxes.data(), areas, sizeof(Box) * n) == 0;
     if (same) return B2_OK;
-    if (n > c->boxCap) {
-        int cap = n < 4096 ? 4096 : n * 2;
+    std::vector<Box> work;
+    if (kind == 0) work.assign((const Box*)areas, (const Box*)areas + n);
+    else {
+        const int R = pbr_fast_strip_rows();
+        for (int k = 0; k < n; ++k) {
+            const b2_box2i& a = areas[k];
+            for (int y = a.min_y; y < a.max_y; y += R)
+                for (int x = a.min_x; x < a.max_x; x += 32)
+                    work.push_back(Box{x, y, x + 32 < a.max_x ? x + 32 : a.max_x, y + R < a.max_y ? y + R : a.max_y});
+        }
+    }
+    const int m = (int)work.size();
+    if (m > c->boxCap) {
+        int cap = m < 16384 ? 16384 : m * 2;
         if (c->dBoxes) { CU(cudaStreamSynchronize(c->stream)); cudaFree(c->dBoxes); cudaFreeHost(c->hBoxes); c->dBoxes = nullptr; c->hBoxes = nullptr; }
         CU(cudaMalloc((void**)&c->dBoxes, sizeof(Box) * cap));
         CU(cudaMallocHost((void**)&c->hBoxes, sizeof(Box) * cap));
         c->boxCap = cap;
     }
-    CU(cudaEventSynchronize(c->boxCopied));  // staging buffer free again?
-    memcpy(c->hBoxes, areas, sizeof(Box) * n);
-    CU(cudaMemcpyAsync(c->dBoxes, c->hBoxes, sizeof(Box) * n, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaEventRecord(c->boxCopied, c->stream));
+    if (m > 0) {
+        CU(cudaEventSynchronize(c->boxCopied));  // staging buffer free again?
+        memcpy(c->hBoxes, work.data(), sizeof(Box) * m);
+        CU(cudaMemcpyAsync(c->dBoxes, c->hBoxes, sizeof(Box) * m, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaEventRecord(c->boxCopied, c->stream));
+    }
     c->lastBoxes.assign((const Box*)areas, (const Box*)areas + n);
+    c->lastBoxKind = kind;
+    c->nDeviceBoxes = m;
     return B2_OK;
 }
 
@@ -423,8 +451,9 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
             if (!boxEmpty(a)) return fail(B2_ERR_INVALID, "compositeTile: area outside this band");
     }
     CU(cudaSetDevice(c->device));
-    int rc = pbrUploadBoxes(c, areas, n);
+    int rc = pbrUploadBoxes(c, areas, n, c->mode == B2_MODE_FAST ? 1 : 0);
     if (rc) return rc;
+    if (c->nDeviceBoxes == 0) return B2_OK;
     PbrArgs A;
     memset(&A, 0, sizeof(A));
     A.nDiffuse = (int)diffuse->levels.size();
@@ -438,7 +467,7 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
     for (int l = 0; l < A.nSky; ++l) A.sky[l] = c->sky->levels[l];
     A.out = c->out;
     A.W = c->W; A.H = c->H;
-    A.boxes = c->dBoxes; A.nBoxes = n;
+    A.boxes = c->dBoxes; A.nBoxes = c->nDeviceBoxes;
     A.rsqrtTab = c->dRsqrt; A.expTab = c->dExpTab;
     const b2pbr_params& p = c->params;
     memcpy(A.light1, p.light1_color, 12); memcpy(A.light2Dir, p.light2_dir, 12); memcpy(A.light2Col, p.light2_color, 12);
@@ -454,7 +483,8 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
         A.skyFY = (float)c->sky->H - 1.0f;
     }
     traceBegin(c, "PBR compositeTile");
-    launch_pbr_exact(A, n, c->stream);
+    if (c->mode == B2_MODE_FAST) launch_pbr_fast(A, c->stream);
+    else launch_pbr_exact(A, c->nDeviceBoxes, c->stream);
     c->launches++;
     traceEnd(c);
     CU(cudaGetLastError());
@@ -541,6 +571,7 @@ int b2pbr_resize(b2pbr* c, int width, int height, int tw, int th) {
     CU(cudaStreamSynchronize(c->stream));
     pbrFreeMaps(c);
     c->lastBoxes.clear();
+    c->lastBoxKind = -1;
     c->W = width; c->H = height; c->tileW = tw; c->tileH = th;
     int y0 = 0, y1 = height, dUp = 0, dDown = 0, zUp = 0, zDown = 0;
     if (c->banded) {
@@ -574,6 +605,11 @@ int b2pbr_resize(b2pbr* c, int width, int height, int tw, int th) {
 int b2pbr_set_params(b2pbr* c, const b2pbr_params* p) {
     if (!c || !p) return fail(B2_ERR_INVALID, "set_params: null");
     c->params = *p;
+    return B2_OK;
+}
+int b2pbr_set_mode(b2pbr* c, int mode) {
+    if (!c || (mode != B2_MODE_FAST && mode != B2_MODE_EXACT)) return fail(B2_ERR_INVALID, "set_mode: bad arguments");
+    c->mode = mode;
     return B2_OK;
 }
 int b2pbr_get_params(const b2pbr* c, b2pbr_params* p) {
@@ -655,7 +691,7 @@ int b2pbr_composite_raw(b2pbr* c, const b2_box2i* areas, int n) {
     if (!c || !c->outAlloc || (n > 0 && !areas)) return fail(B2_ERR_STATE, "composite_raw: bad state");
     if (n <= 0) return B2_OK;
     CU(cudaSetDevice(c->device));
-    int rc = pbrUploadBoxes(c, areas, n);
+    int rc = pbrUploadBoxes(c, areas, n, 0);
     if (rc) return rc;
     launch_copy_diffuse(c->out, c->diffuse->levels[0], c->dBoxes, n, n, c->stream);
     c->launches++;
@@ -670,7 +706,10 @@ int b2pbr_download(b2pbr* c, void* host, size_t host_pitch, const b2_box2i* rect
         const b2_box2i& r = rects[k];
         if (!boxSorted(r) || r.min_x < 0 || r.min_y < c->out.y0 || r.max_x > c->W || r.max_y > c->out.y0 + c->out.rows)
             return fail(B2_ERR_INVALID, "download: rectangle outside the stored frame");
-        if (boxEmpty(r)) continue;
+    }
+    std::vector<b2_box2i> merged;
+    mergeRects(rects, n, merged);
+    for (const b2_box2i& r : merged) {
         CU(cudaMemcpy2DAsync((uint8_t*)host + (size_t)r.min_y * host_pitch + (size_t)r.min_x * 4, host_pitch,
                              c->out.base + (size_t)(r.min_y - c->out.y0) * c->out.pitch + (size_t)r.min_x * 4, (size_t)c->out.pitch,
                              (size_t)boxW(r) * 4, (size_t)boxH(r), cudaMemcpyDeviceToHost, c->stream));
@@ -686,7 +725,10 @@ int b2pbr_download_swizzled(b2pbr* c, int pf, void* host, size_t host_pitch, con
         const b2_box2i& r = rects[k];
         if (!boxSorted(r) || r.min_x < 0 || r.min_y < c->out.y0 || r.max_x > c->W || r.max_y > c->out.y0 + c->out.rows)
             return fail(B2_ERR_INVALID, "download_swizzled: rectangle outside the stored frame");
-        if (boxEmpty(r)) continue;
+    }
+    std::vector<b2_box2i> merged;
+    mergeRects(rects, n, merged);
+    for (const b2_box2i& r : merged) {
         launch_swizzle(c->swz, c->out, toBox(r), pf, c->stream);
         c->launches++;
         CU(cudaMemcpy2DAsync((uint8_t*)host + (size_t)r.min_y * host_pitch + (size_t)r.min_x * 4, host_pitch,

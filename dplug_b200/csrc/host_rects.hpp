@@ -79,6 +79,30 @@ inline void removeOverlappingAreas(std::vector<b2_box2i>& boxes, std::vector<b2_
     }
 }
 
+// Coalesces a list of disjoint rectangles for bulk copies: horizontally adjacent boxes with the same rows are
+// joined, then vertically adjacent spans with the same columns (a full-frame 64x64 tile list collapses to one
+// rectangle).  Coverage is unchanged; used only to batch host<->device transfers.
+inline void mergeRects(const b2_box2i* rects, int n, std::vector<b2_box2i>& out) {
+    std::vector<b2_box2i> v;
+    for (int i = 0; i < n; ++i)
+        if (boxW(rects[i]) > 0 && boxH(rects[i]) > 0) v.push_back(rects[i]);
+    auto pass = [&](bool horizontal) {
+        std::vector<b2_box2i> w;
+        for (const b2_box2i& r : v) {
+            bool joined = false;
+            for (auto it = w.rbegin(); it != w.rend() && (it - w.rbegin()) < 64; ++it) {
+                if (horizontal && it->min_y == r.min_y && it->max_y == r.max_y && it->max_x == r.min_x) { it->max_x = r.max_x; joined = true; break; }
+                if (!horizontal && it->min_x == r.min_x && it->max_x == r.max_x && it->max_y == r.min_y) { it->max_y = r.max_y; joined = true; break; }
+            }
+            if (!joined) w.push_back(r);
+        }
+        v.swap(w);
+    };
+    pass(true);
+    pass(false);
+    out.swap(v);
+}
+
 inline b2_box2i growRect(b2_box2i r, int margin, int width, int height) {
     int xmin = r.min_x - margin, ymin = r.min_y - margin, xmax = r.max_x + margin, ymax = r.max_y + margin;
     if (xmin < 0) xmin = 0;

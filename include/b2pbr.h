@@ -44,6 +44,9 @@ enum {
 };
 /* the maps GUIGraphics owns and lends to the compositor — gui/dplug/gui/graphics.d:117-122 */
 enum { B2_MAP_DIFFUSE = 0, B2_MAP_MATERIAL = 1, B2_MAP_DEPTH = 2 };
+/* lighting kernels: FAST = throughput kernel (FMA / MUFU, +-1 LSB contract); EXACT = the reference's IEEE operation
+ * order, bit-identical to the CPU restatement (several times slower; the device-side yardstick) */
+enum { B2_MODE_FAST = 0, B2_MODE_EXACT = 1 };
 /* window pixel orders for the fused post-composite swizzle — window/dplug/window/window.d WindowPixelFormat */
 enum { B2_PF_RGBA8 = 0, B2_PF_BGRA8 = 1, B2_PF_ARGB8 = 2 };
 
@@ -140,6 +143,8 @@ int b2pbr_set_stream(b2pbr*, void* cuda_stream);
 int b2pbr_resize(b2pbr*, int width, int height, int area_max_width, int area_max_height);
 int b2pbr_set_params(b2pbr*, const b2pbr_params*);
 int b2pbr_get_params(const b2pbr*, b2pbr_params*);
+/* selects the lighting kernel compositeTile launches (B2_MODE_*; default B2_MODE_FAST) */
+int b2pbr_set_mode(b2pbr*, int mode);
 /* PassSkyboxReflections.setSkybox(OwnedImage!RGBA) — legacypbr.d:861-870: copies the host image to the
  * device, builds Mipmap!RGBA(12, image) and generateMipmaps(Quality.box).  rgba == NULL removes the skybox.
  * (The reference takes ownership of the image; here the caller keeps it.) */

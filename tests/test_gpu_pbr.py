@@ -10,10 +10,14 @@ pytestmark = pytest.mark.gpu
 TOL_LSB = 1
 
 
-def _setup(b2, oracle, W, H, depth_kind="smooth", seed=synth.SEED, sky=True, params=None, threads=8):
+MODES = [0, 1]  # B2_MODE_FAST (what ships by default), B2_MODE_EXACT
+
+
+def _setup(b2, oracle, W, H, depth_kind="smooth", seed=synth.SEED, sky=True, params=None, threads=8, mode=0):
     d, m, z = synth.frame(W, H, seed, depth_kind)
     comp = b2.PBRCompositor(0)
     comp.resizeBuffers(W, H, 64, 64)
+    comp.setMode(mode)
     ref = oracle.Graphics(W, H, numThreads=threads)
     if sky:
         s = synth.skybox(256, 192, seed)
@@ -31,9 +35,11 @@ def _compare(got, exp, what=""):
     return int(diff.max()), float((diff > 0).mean())
 
 
-@pytest.mark.parametrize("W,H,kind", [(620, 330, "smooth"), (620, 330, "noise"), (257, 131, "smooth"), (64, 64, "noise"), (33, 17, "smooth")])
-def test_full_frame_parity(b2, oracle, W, H, kind):
-    comp, ref, _ = _setup(b2, oracle, W, H, kind)
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("W,H,kind", [(620, 330, "smooth"), (620, 330, "noise"), (257, 131, "smooth"), (64, 64, "noise"), (33, 17, "smooth"),
+                                      (1, 1, "smooth"), (3, 70, "noise"), (100, 2, "smooth")])
+def test_full_frame_parity(b2, oracle, W, H, kind, mode):
+    comp, ref, _ = _setup(b2, oracle, W, H, kind, mode=mode)
     whole = [(0, 0, W, H)]
     comp.regenerateMipmaps(whole)
     comp.compositeGUI(whole)
@@ -48,7 +54,10 @@ def test_full_frame_parity(b2, oracle, W, H, kind):
             assert np.array_equal(comp.depthMap.download(level), ref.depthMap.download(level)), level
     mx, frac = _compare(got, exp, "%dx%d %s" % (W, H, kind))
     assert (got[..., 3] == 255).all()
-    assert mx == 0, "exact kernel expected bit-identical output, got max %d LSB on %.4f of channels" % (mx, frac)
+    if mode == 1:
+        assert mx == 0, "exact kernel expected bit-identical output, got max %d LSB on %.4f of channels" % (mx, frac)
+    else:
+        assert frac < 0.02, "fast kernel: %.4f of channels differ by 1 LSB (expected a truncation-boundary trickle)" % frac
 
 
 def test_distort_lighting_overrides(b2, oracle):
@@ -72,14 +81,18 @@ def test_distort_lighting_overrides(b2, oracle):
     p.light3_color = v3(0.2, 0.2, 0.2, 0.84)
     p.ambient_light = 0.042
     p.skybox_amount = 0.56
-    comp, ref, _ = _setup(b2, oracle, 620, 330, params=p)
-    whole = [(0, 0, 620, 330)]
-    comp.regenerateMipmaps(whole); comp.compositeGUI(whole)
-    _compare(comp.download(), ref.fullFrame(), "distort lights")
+    exp = None
+    for mode in MODES:
+        comp, ref, _ = _setup(b2, oracle, 620, 330, params=p, mode=mode)
+        whole = [(0, 0, 620, 330)]
+        comp.regenerateMipmaps(whole); comp.compositeGUI(whole)
+        exp = ref.fullFrame() if exp is None else exp
+        _compare(comp.download(), exp, "distort lights mode %d" % mode)
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("mask", [0xff & ~(1 << k) for k in range(7)] + [0x81, 0x83, 0x91, 0xa1, 0xc1])
-def test_pass_masks(b2, oracle, mask):
+def test_pass_masks(b2, oracle, mask, mode):
     """CompositorPass.setActive (compositor.d:222-236): every single pass switched off, and single-pass set-ups.
     (With the normal pass off the reference reads stale scratch; only masks that keep it on or use no normal
     consumer are compared.)"""
@@ -88,28 +101,31 @@ def test_pass_masks(b2, oracle, mask):
     p = b2.default_params()
     p.pass_active_mask = mask
     W, H = 200, 120
-    comp, ref, _ = _setup(b2, oracle, W, H, params=p)
+    comp, ref, _ = _setup(b2, oracle, W, H, params=p, mode=mode)
     whole = [(0, 0, W, H)]
     comp.regenerateMipmaps(whole); comp.compositeGUI(whole)
     _compare(comp.download(), ref.fullFrame(), "mask %02x" % mask)
 
 
-def test_no_skybox(b2, oracle):
-    comp, ref, _ = _setup(b2, oracle, 150, 90, sky=False)
+@pytest.mark.parametrize("mode", MODES)
+def test_no_skybox(b2, oracle, mode):
+    comp, ref, _ = _setup(b2, oracle, 150, 90, sky=False, mode=mode)
     whole = [(0, 0, 150, 90)]
     comp.regenerateMipmaps(whole); comp.compositeGUI(whole)
     _compare(comp.download(), ref.fullFrame(), "no skybox")
 
 
-def test_dirty_rect_update(b2, oracle):
+@pytest.mark.parametrize("mode", MODES)
+def test_dirty_rect_update(b2, oracle, mode):
     """One frame fully composited, then a widget-sized change: dirty rect -> regenerateMipmaps(rect) ->
     compositeGUI(rect grown by the update margin) on both back ends (graphics.d:884-1002,1338-1423).
     Pixels outside the composited tiles must be untouched."""
     W, H = 620, 330
-    comp, ref, (d, m, z) = _setup(b2, oracle, W, H)
+    comp, ref, (d, m, z) = _setup(b2, oracle, W, H, mode=mode)
     whole = [(0, 0, W, H)]
     comp.regenerateMipmaps(whole); comp.compositeGUI(whole)
     exp0 = ref.fullFrame()
+    _compare(comp.download(), exp0, "initial frame")
     rng = np.random.default_rng(3)
     for it in range(6):
         x0, y0 = int(rng.integers(0, W - 40)), int(rng.integers(0, H - 40))
@@ -179,6 +195,13 @@ def test_4k_frame_properties_and_sampled_parity(b2, oracle):
     comp.regenerateMipmaps(whole)
     comp.compositeGUI(whole)
     got = comp.download()
+    # the whole frame against the exact-arithmetic kernel (bit-identical to the oracle on every size tested)
+    comp.setMode(1)
+    comp.compositeGUI(whole)
+    exact = comp.download()
+    comp.setMode(0)
+    mx, frac = _compare(got, exact, "4K fast vs exact kernel")
+    print("4K fast vs exact: max %d LSB, %.5f of channels differ" % (mx, frac))
     assert (got[..., 3] == 255).all()
     comp.compositeTile(None, b2.tileAreas(whole, 17, 13))
     assert np.array_equal(comp.download(), got)
