@@ -273,7 +273,7 @@ def run_b200(args, W, H, desc):
                    "l2": "inputs larger than L2: %d independent frames (%.0f MB) visited round-robin" % (R, R * B / 1e6),
                    "parallelism": "independent frames per GPU, no collective" if world > 1 else "1 GPU"},
         "frame_roofline_frac": (B * args.steps / (ms * 1e-3) / 1e9) / peak,
-        "roofline": {"bound": "hbm", "kernel": "k_pbr_exact (lighting)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_pbr_fast (fused lighting, 8 passes)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": B, "launch_ms": light_ms},
         "e2e": {"value": world * W * H * e2e_steps / e2e_s / 1e6, "unit": "Mpix/s",

@@ -451,7 +451,10 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
             if (!boxEmpty(a)) return fail(B2_ERR_INVALID, "compositeTile: area outside this band");
     }
     CU(cudaSetDevice(c->device));
-    int rc = pbrUploadBoxes(c, areas, n, c->mode == B2_MODE_FAST ? 1 : 0);
+    // the throughput kernel assumes full pyramids (diffuse levels 0..5, depth 0..4: any canvas >= 32x32);
+    // smaller canvases are shaded by the exact kernel
+    const bool fast = c->mode == B2_MODE_FAST && (int)diffuse->levels.size() >= kMaxDiffuseLevels && (int)depth->levels.size() >= kMaxDepthLevels;
+    int rc = pbrUploadBoxes(c, areas, n, fast ? 1 : 0);
     if (rc) return rc;
     if (c->nDeviceBoxes == 0) return B2_OK;
     PbrArgs A;
@@ -483,7 +486,7 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
         A.skyFY = (float)c->sky->H - 1.0f;
     }
     traceBegin(c, "PBR compositeTile");
-    if (c->mode == B2_MODE_FAST) launch_pbr_fast(A, c->stream);
+    if (fast) launch_pbr_fast(A, c->stream);
     else launch_pbr_exact(A, c->nDeviceBoxes, c->stream);
     c->launches++;
     traceEnd(c);

@@ -3,36 +3,63 @@
 // Same eight passes as gui/dplug/gui/legacypbr.d:269-1108, fused, but organised for the SM instead of for
 // a 64x64 CPU tile:
 //
-//   * work item = one WARP = a strip of 32 adjacent columns x up to STRIP_ROWS rows of one GUI tile; a lane
-//     owns one column and walks down it, so every per-row quantity that depends only on j is warp-uniform
-//     and every per-column quantity is computed once per strip;
-//   * level-0 depth of the strip (+10 columns left/right, 10 rows up, 1 down: the reach of the oblique
-//     shadow, legacypbr.d:525-534, and of the 3x3 normal stencil, legacypbr.d:301-314) is staged once per
-//     warp in shared memory as float with clamp-to-edge addressing (= the reference's replicated border);
+//   * work item = one WARP = a strip of 32 adjacent columns x up to 32 rows of one GUI tile; a lane owns one
+//     column and walks down it, so per-row quantities are warp-uniform and per-column ones are computed once;
+//   * everything a strip samples besides its own pixels is staged ONCE per warp in shared memory, with all
+//     global loads issued back to back (one exposed latency per strip instead of several per row):
+//       - level-0 depth, +10 columns left/right, 10 rows up, 1 down (reach of the oblique shadow,
+//         legacypbr.d:525-534, and of the 3x3 normal stencil, legacypbr.d:301-314), as float, with
+//         clamp-to-edge addressing (= the reference's replicated border, graphics.d:1121-1126);
+//       - the texel windows of diffuse levels 1..5 and depth levels 1..4 the strip's samplers touch;
+//       - a per-row table of the vertical sampler set-up (texel rows, fractions, Catmull-Rom weights);
 //   * the mip samplers (Mipmap.linearSample / cubicSample, graphics/dplug/graphics/mipmap.d:167-496) are
-//     evaluated separably: the horizontal interpolation of a texel row is done once and reused for the
-//     2^level rows that share it ("rolling rows" in registers), the vertical bicubic of levels 4/5 is a
-//     Horner polynomial per texel interval;
+//     evaluated separably: the horizontal interpolation of a texel row is done once per lane and reused for
+//     the 2^level rows that share it ("rolling rows" in registers);
+//   * this row's diffuse / material pixels are prefetched while the previous row is shaded;
 //   * 8/16-bit -> float conversions use byte-permute + magic-number subtraction (FMA pipe) instead of I2F
-//     (quarter-rate XU pipe), pow / reciprocal use MUFU.
+//     (quarter-rate XU pipe); pow / reciprocal use MUFU.
 //
 // Numerical contract: +-1 LSB per 8-bit channel against the reference arithmetic (BASELINE.json).  The
 // three RSQRTSS operands per pixel are computed with the reference's exact IEEE sequence (no FMA, same
 // order) because the table-driven RSQRTSS is discontinuous and Blinn-Phong exponents up to 548 amplify
 // it; everything downstream may use FMA / MUFU (relative error ~1e-6).
+//
+// Precondition (checked by the host): full pyramids, i.e. diffuse has levels 0..5 and depth 0..4 (every canvas
+// of at least 32x32 pixels).  Smaller canvases take the exact kernel.
 #include "pbr_math.cuh"
 
 namespace b2 {
 
-#ifndef B2_STRIP_ROWS
-#define B2_STRIP_ROWS 32
-#endif
-constexpr int STRIP_ROWS = B2_STRIP_ROWS;
+constexpr int STRIP_ROWS = 32;
 constexpr int HALO_X = 10;                     // shadow reach left/right
 constexpr int HALO_UP = 10;                    // shadow reach upwards
 constexpr int TILE_COLS = 32 + 2 * HALO_X + 2; // +2: the staged window starts at an even column
 constexpr int TILE_ROWS = STRIP_ROWS + HALO_UP + 1;
 constexpr int WARPS_PER_CTA = 4;
+#ifndef B2_MIN_CTAS
+#define B2_MIN_CTAS 3
+#endif
+
+// window extents: a bilinear sampler of level l touches at most (32 >> l) + 2 texels along 32 pixels, a
+// bicubic one (32 >> l) + 4
+constexpr int W1 = 18, W2 = 10, W3 = 6, WZ4 = 4, WC4 = 6, WC5 = 5;
+
+struct RowSetup {            // vertical sampler set-up of one row; texel rows are relative to the staged windows
+    int iy[4], iy1[4];       // levels 1, 2, 3 (diffuse and depth share them) and depth level 4
+    float fy[4];
+    int ib4, ib5;            // bicubic interval (floor(y_s) + 1) of diffuse levels 4 and 5
+    float wy4[4], wy5[4];    // Catmull-Rom weights of the four rows
+    int pad[2];
+};
+static_assert(sizeof(RowSetup) % 16 == 0, "RowSetup is read with 128-bit shared loads");
+
+struct alignas(16) WarpSmem {
+    RowSetup rows[STRIP_ROWS];
+    float depth[TILE_ROWS][TILE_COLS];
+    uint32_t d1[W1][W1], d2[W2][W2], d3[W3][W3], d4[WC4][WC4], d5[WC5][WC5];
+    uint16_t z1[W1][W1], z2[W2][W2], z3[W3][W3], z4[WZ4][WZ4];
+};
+static_assert(sizeof(WarpSmem) % 16 == 0, "per-warp shared block keeps 16-byte alignment");
 
 struct F3 { float x, y, z; };
 __device__ __forceinline__ F3 operator+(F3 a, F3 b) { return F3{a.x + b.x, a.y + b.y, a.z + b.z}; }
@@ -69,19 +96,18 @@ __device__ __forceinline__ uint32_t cvtSatU8(float f) {  // truncate, clamp to [
     return r & 0xffu;
 }
 
-// horizontal set-up of a sampler for one column (lane-constant during a strip)
-struct XLin { int ix, ix1; float fx; };
-__device__ __forceinline__ XLin xLinear(float scale, int i, int w) {
-    float x = ((float)i + 0.5f) * scale - 0.5f;  // mipmap.d:309-314 (exact: powers of two and small integers)
-    x = x < 0 ? 0.f : x;
-    XLin s;
-    int ix = __float2int_rz(x);
-    s.fx = x - (float)ix;
-    s.ix = min(ix, w - 1);
-    s.ix1 = min(s.ix + 1, w - 1);
+// ---- sampler coordinates.  (p + 0.5) * 2^-l - 0.5 == n / 2^(l+1) with n = 2p + 1 - 2^l: integer shifts give
+// the texel index and the fraction exactly as the reference's float arithmetic does (which is exact here).
+struct Lin { int i0, i1; float f; };
+__device__ __forceinline__ Lin linCoord(int l, int p, int size) {  // Mipmap.linearSample, mipmap.d:309-339
+    int n = max(2 * p + 1 - (1 << l), 0);  // negative coordinate -> 0
+    Lin s;
+    int i = n >> (l + 1);
+    s.f = (float)(n & ((2 << l) - 1)) * levelScale(l + 1);  // fraction taken before the upper clamp
+    s.i0 = min(i, size - 1);
+    s.i1 = min(s.i0 + 1, size - 1);
     return s;
 }
-struct XCub { int xi[4]; float w[4]; };
 __device__ __forceinline__ void catmullRomWeights(float t, float w[4]) {
     // cubicInterp (mipmap.d:263-270) regrouped per sample: p0*w0 + p1*w1 + p2*w2 + p3*w3
     float t2 = t * t, t3 = t2 * t;
@@ -90,193 +116,163 @@ __device__ __forceinline__ void catmullRomWeights(float t, float w[4]) {
     w[2] = 0.5f * t + 2.0f * t2 - 1.5f * t3;
     w[3] = -0.5f * t2 + 0.5f * t3;
 }
-__device__ __forceinline__ XCub xCubic(float scale, int i, int w) {
-    float x = ((float)i + 0.5f) * scale - 0.5f;  // mipmap.d:182-204
-    XCub s;
+// Mipmap.cubicSample, mipmap.d:182-204: y_s + 1 = (n + 2^(l+1)) / 2^(l+1) is always positive, so the truncations
+// are floors; ib = floor(y_s) + 1; the four texels are clamp(ib - 2 + k)
+__device__ __forceinline__ void cubCoord(int l, int p, int& ib, float& t) {
+    const int n1 = 2 * p + 1 - (1 << l) + (2 << l);
+    ib = n1 >> (l + 1);
+    t = (float)(n1 & ((2 << l) - 1)) * levelScale(l + 1);
+}
+
+// copies the window [y0, y0 + WH) x [x0, x0 + WW) of a level into shared memory, clamped to the level
+template <typename T, int WW, int WH>
+__device__ __forceinline__ void stageWindow(T (*dst)[WW], const DevLevel& L, int x0, int y0, int lane) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) s.xi[k] = max(0, min(__float2int_rz(x + (float)(k - 1)), w - 1));
-    float a = x + 1.0f;
-    a = a - (float)__float2int_rz(a);
-    catmullRomWeights(a, s.w);
-    return s;
-}
-
-// vertical set-up of a sampler for one row.  (j + 0.5) * 2^-l - 0.5 == n / 2^(l+1) with n = 2j + 1 - 2^l, so the
-// texel row and the fraction come from integer shifts on warp-uniform values (uniform datapath); the float
-// results are bit-identical to the reference's float arithmetic, which is exact for these operands.
-struct YLin { int iy, iy1; float fy; };
-__device__ __forceinline__ YLin yLinear(int l, int j, int h) {
-    int n = max(2 * j + 1 - (1 << l), 0);                      // y < 0 -> 0 (mipmap.d:315-316)
-    YLin s;
-    int iy = n >> (l + 1);
-    s.fy = (float)(n & ((2 << l) - 1)) * levelScale(l + 1);    // fraction taken before the upper clamp
-    s.iy = min(iy, h - 1);
-    s.iy1 = min(s.iy + 1, h - 1);
-    return s;
-}
-
-// ---- rolling rows: bilinear RGB level (diffuse levels 1..3) ------------------------------------------
-struct RollRGB {
-    int rowA, rowB;
-    F3 a, d;  // value of row A and (row B - row A), both already interpolated horizontally for this column
-};
-__device__ __forceinline__ F3 hrowRGB(const DevLevel& L, const XLin& xs, int row) {
-    const uint32_t* p = rowPtr<uint32_t>(L, row);
-    F3 A = rgbOf(__ldg(p + xs.ix)), B = rgbOf(__ldg(p + xs.ix1));
-    return fma3(xs.fx, B - A, A);
-}
-__device__ __forceinline__ F3 sampleRollRGB(RollRGB& r, const DevLevel& L, const XLin& xs, const YLin& ys) {
-    if (ys.iy != r.rowA || ys.iy1 != r.rowB) {  // warp-uniform
-        F3 na = (ys.iy == r.rowB) ? (r.a + r.d) : ((ys.iy == r.rowA) ? r.a : hrowRGB(L, xs, ys.iy));
-        F3 nb = (ys.iy1 == ys.iy) ? na : hrowRGB(L, xs, ys.iy1);
-        r.a = na; r.d = nb - na;
-        r.rowA = ys.iy; r.rowB = ys.iy1;
+    for (int idx = lane; idx < WW * WH; idx += 32) {
+        const int r = idx / WW, c = idx - r * WW;
+        const int gy = max(0, min(y0 + r, L.h - 1)), gx = max(0, min(x0 + c, L.w - 1));
+        dst[r][c] = __ldg(rowPtr<T>(L, gy) + gx);
     }
-    return fma3(ys.fy, r.d, r.a);
-}
-
-// ---- rolling rows: bilinear L16 level (depth levels 1..4) ----------------------------------------------
-struct RollZ { int rowA, rowB; float a, d; };
-__device__ __forceinline__ float hrowZ(const DevLevel& L, const XLin& xs, int row) {
-    const uint16_t* p = rowPtr<uint16_t>(L, row);
-    float A = u16ToFloat(__ldg(p + xs.ix)), B = u16ToFloat(__ldg(p + xs.ix1));
-    return fmaf(xs.fx, B - A, A);
-}
-__device__ __forceinline__ float sampleRollZ(RollZ& r, const DevLevel& L, const XLin& xs, const YLin& ys) {
-    if (ys.iy != r.rowA || ys.iy1 != r.rowB) {
-        float na = (ys.iy == r.rowB) ? (r.a + r.d) : ((ys.iy == r.rowA) ? r.a : hrowZ(L, xs, ys.iy));
-        float nb = (ys.iy1 == ys.iy) ? na : hrowZ(L, xs, ys.iy1);
-        r.a = na; r.d = nb - na;
-        r.rowA = ys.iy; r.rowB = ys.iy1;
-    }
-    return fmaf(ys.fy, r.d, r.a);
-}
-
-// ---- rolling rows: bicubic RGB level (diffuse levels 4, 5) ------------------------------------------------
-struct RollCub {
-    int base;     // trunc(y_s) of the interval the polynomial below is valid for (INT_MIN = none)
-    F3 c0, c1, c2, c3;
-};
-__device__ __forceinline__ F3 hrowCub(const DevLevel& L, const XCub& xs, int row) {
-    const uint32_t* p = rowPtr<uint32_t>(L, row);
-    F3 r = rgbOf(__ldg(p + xs.xi[0])) * xs.w[0];
-    r = fma3(xs.w[1], rgbOf(__ldg(p + xs.xi[1])), r);
-    r = fma3(xs.w[2], rgbOf(__ldg(p + xs.xi[2])), r);
-    r = fma3(xs.w[3], rgbOf(__ldg(p + xs.xi[3])), r);
-    return r;
-}
-__device__ __forceinline__ F3 sampleRollCub(RollCub& r, const DevLevel& L, const XCub& xs, int l, int j) {
-    // y_s + 1 = (n + 2^(l+1)) / 2^(l+1), n = 2j + 1 - 2^l (mipmap.d:182-204); always positive, so the
-    // reference's truncations are floors and everything below is exact integer arithmetic on uniform values
-    const int n1 = 2 * j + 1 - (1 << l) + (2 << l);
-    const int ib = n1 >> (l + 1);
-    const float t = (float)(n1 & ((2 << l) - 1)) * levelScale(l + 1);
-    if (ib != r.base) {
-        const int h = L.h;
-        F3 p[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int row = max(0, min(ib - 2 + k, h - 1));   // trunc(y_s + k - 1) clamped (mipmap.d:188-193)
-            p[k] = hrowCub(L, xs, row);
-        }
-        // Catmull-Rom as a polynomial in t (mipmap.d:263-270)
-        r.c0 = p[1];
-        r.c1 = (p[2] - p[0]) * 0.5f;
-        r.c2 = F3{p[0].x - 2.5f * p[1].x + 2.0f * p[2].x - 0.5f * p[3].x, p[0].y - 2.5f * p[1].y + 2.0f * p[2].y - 0.5f * p[3].y,
-                  p[0].z - 2.5f * p[1].z + 2.0f * p[2].z - 0.5f * p[3].z};
-        r.c3 = F3{-0.5f * p[0].x + 1.5f * p[1].x - 1.5f * p[2].x + 0.5f * p[3].x, -0.5f * p[0].y + 1.5f * p[1].y - 1.5f * p[2].y + 0.5f * p[3].y,
-                  -0.5f * p[0].z + 1.5f * p[1].z - 1.5f * p[2].z + 0.5f * p[3].z};
-        r.base = ib;
-    }
-    F3 v = fma3(t, r.c3, r.c2);
-    v = fma3(t, v, r.c1);
-    v = fma3(t, v, r.c0);
-    // clamp_0_to_65535 (mipmap.d:250-261); 8-bit sources cannot reach the upper bound
-    return F3{fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f)};
-}
-
-// ---- skybox: Mipmap!RGBA.linearSample on one level, RGB only (mipmap.d:293-385) ------------------------
-__device__ __forceinline__ F3 skySample(const PbrArgs& P, int level, float x, float y) {
-    level = max(0, min(level, P.nSky - 1));
-    const DevLevel& L = P.sky[level];
-    Bilin s = bilinSetup(levelScale(level), x, y, L.w, L.h);
-    const uint32_t* r0 = rowPtr<uint32_t>(L, s.iy);
-    const uint32_t* r1 = rowPtr<uint32_t>(L, s.iy1);
-    uint32_t a = __ldg(r0 + s.ix), b = __ldg(r0 + s.ix1), c = __ldg(r1 + s.ix), d = __ldg(r1 + s.ix1);
-    F3 A = rgbOf(a), B = rgbOf(b), C = rgbOf(c), D = rgbOf(d);
-    F3 up = fma3(s.fx, B - A, A);
-    F3 down = fma3(s.fx, D - C, C);
-    return fma3(s.fy, down - up, up);
-}
-
-// exact (non-fused, reference-ordered) RSQRTSS operand helpers
-__device__ __forceinline__ float rsqrtArgExact(float x, float y, float z) {
-    // _mm_fast_normalize_ps: squared = v*v; x2 + y2 + z2 + w2 with w = 0 (ransac.d:41-42)
-    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));  // (+0 is the identity here)
 }
 
 template <bool HAS_SKY>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_pbr_fast(const __grid_constant__ PbrArgs P) {
-    __shared__ float sDepth[WARPS_PER_CTA][TILE_ROWS][TILE_COLS];
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(const __grid_constant__ PbrArgs P) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int item = blockIdx.x * WARPS_PER_CTA + warp;
     if (item >= P.nBoxes) return;
-    const Box box = P.boxes[item];  // one strip: at most 32 columns x STRIP_ROWS rows
+    WarpSmem& S = reinterpret_cast<WarpSmem*>(smemRaw)[warp];
+    const Box box = P.boxes[item];  // one strip: at most 32 columns x 32 rows
     const int W = P.W, H = P.H;
     const DevLevel& D0 = P.depth[0];
+    const int xLast = box.maxx - 1, yLast = box.maxy - 1;
+
+    // ---------------------------------------------------------------- prefetch the first row's pixels
+    const int i = box.minx + lane;
+    const bool active = i < box.maxx;
+    const int ic = min(i, xLast);  // inactive lanes shadow the last column (no divergence, no stores)
+    uint32_t diffuseNext = __ldg(rowPtr<uint32_t>(P.diffuse[0], box.miny) + ic);
+    uint32_t materialNext = __ldg(rowPtr<uint32_t>(P.material, box.miny) + ic);
+
+    // ---------------------------------------------------------------- stage the mip windows
+    // window origins: first texel the first column / row of the strip touches
+    const int ox1 = linCoord(1, box.minx, P.diffuse[1].w).i0, oy1 = linCoord(1, box.miny, P.diffuse[1].h).i0;
+    const int ox2 = linCoord(2, box.minx, P.diffuse[2].w).i0, oy2 = linCoord(2, box.miny, P.diffuse[2].h).i0;
+    const int ox3 = linCoord(3, box.minx, P.diffuse[3].w).i0, oy3 = linCoord(3, box.miny, P.diffuse[3].h).i0;
+    const int oxz4 = linCoord(4, box.minx, P.depth[4].w).i0, oyz4 = linCoord(4, box.miny, P.depth[4].h).i0;
+    int ibx, iby; float tt;
+    cubCoord(4, box.minx, ibx, tt); cubCoord(4, box.miny, iby, tt);
+    const int ox4 = max(0, min(ibx - 2, P.diffuse[4].w - 1)), oy4 = max(0, min(iby - 2, P.diffuse[4].h - 1));
+    cubCoord(5, box.minx, ibx, tt); cubCoord(5, box.miny, iby, tt);
+    const int ox5 = max(0, min(ibx - 2, P.diffuse[5].w - 1)), oy5 = max(0, min(iby - 2, P.diffuse[5].h - 1));
+
+    stageWindow<uint32_t, W1, W1>(S.d1, P.diffuse[1], ox1, oy1, lane);
+    stageWindow<uint16_t, W1, W1>(S.z1, P.depth[1], ox1, oy1, lane);
+    stageWindow<uint32_t, W2, W2>(S.d2, P.diffuse[2], ox2, oy2, lane);
+    stageWindow<uint16_t, W2, W2>(S.z2, P.depth[2], ox2, oy2, lane);
+    stageWindow<uint32_t, W3, W3>(S.d3, P.diffuse[3], ox3, oy3, lane);
+    stageWindow<uint16_t, W3, W3>(S.z3, P.depth[3], ox3, oy3, lane);
+    stageWindow<uint32_t, WC4, WC4>(S.d4, P.diffuse[4], ox4, oy4, lane);
+    stageWindow<uint16_t, WZ4, WZ4>(S.z4, P.depth[4], oxz4, oyz4, lane);
+    stageWindow<uint32_t, WC5, WC5>(S.d5, P.diffuse[5], ox5, oy5, lane);
 
     // ---------------------------------------------------------------- stage the depth window
     // columns [cx0, cx0 + TILE_COLS), rows [box.miny - 10, box.maxy + 1), clamped to the image
     const int cx0 = (box.minx - HALO_X) & ~1;
     const int ry0 = box.miny - HALO_UP;
     const int nRows = (box.maxy - box.miny) + HALO_UP + 1;
-    float(*tile)[TILE_COLS] = sDepth[warp];
-    for (int r = 0; r < nRows; ++r) {
-        const int gy = max(0, min(ry0 + r, H - 1));
-        const uint16_t* src = rowPtr<uint16_t>(D0, gy);
-        const int c = 2 * lane;  // each lane converts a pair of texels
-        if (c < TILE_COLS) {
-            const int gx = cx0 + c;
+    if (2 * lane < TILE_COLS) {
+        const int c = 2 * lane;  // each lane converts a pair of texels per row
+        const int gx = cx0 + c;
+        const bool pairOk = gx >= 0 && gx + 1 < W;
+        const int gxa = max(0, min(gx, W - 1)), gxb = max(0, min(gx + 1, W - 1));
+#pragma unroll 4
+        for (int r = 0; r < nRows; ++r) {
+            const int gy = max(0, min(ry0 + r, H - 1));
+            const uint16_t* src = rowPtr<uint16_t>(D0, gy);
             float f0, f1;
-            if (gx >= 0 && gx + 1 < W) {
+            if (pairOk) {
                 uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + gx));
                 f0 = u16ToFloat(v & 0xffffu);
                 f1 = u16ToFloat(v >> 16);
             } else {
-                f0 = u16ToFloat(__ldg(src + max(0, min(gx, W - 1))));
-                f1 = u16ToFloat(__ldg(src + max(0, min(gx + 1, W - 1))));
+                f0 = u16ToFloat(__ldg(src + gxa));
+                f1 = u16ToFloat(__ldg(src + gxb));
             }
-            *reinterpret_cast<float2*>(&tile[r][c]) = make_float2(f0, f1);
+            *reinterpret_cast<float2*>(&S.depth[r][c]) = make_float2(f0, f1);
         }
+    }
+
+    // ---------------------------------------------------------------- per-row table: lane k prepares row miny + k
+    if (box.miny + lane <= yLast) {
+        const int j = box.miny + lane;
+        RowSetup rs;
+        const int oy[4] = {oy1, oy2, oy3, oyz4};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            Lin y = linCoord(k + 1, j, k < 3 ? P.diffuse[k + 1].h : P.depth[4].h);
+            rs.iy[k] = y.i0 - oy[k]; rs.iy1[k] = y.i1 - oy[k]; rs.fy[k] = y.f;
+        }
+        float t;
+        cubCoord(4, j, rs.ib4, t); catmullRomWeights(t, rs.wy4);
+        cubCoord(5, j, rs.ib5, t); catmullRomWeights(t, rs.wy5);
+        rs.pad[0] = rs.pad[1] = 0;
+        S.rows[lane] = rs;
     }
     __syncwarp();
 
-    const int i = box.minx + lane;
-    const bool active = i < box.maxx;
-    const int ic = min(i, box.maxx - 1);        // inactive lanes shadow the last column (no divergence, no stores)
-    const int tx = ic - cx0;                    // column of this lane inside the staged window
-    const uint32_t mask = P.passMask;
+    // ---------------------------------------------------------------- per-column set-up (window-relative)
+    const Lin c1 = linCoord(1, ic, P.diffuse[1].w), c2 = linCoord(2, ic, P.diffuse[2].w), c3 = linCoord(3, ic, P.diffuse[3].w);
+    const Lin cz4 = linCoord(4, ic, P.depth[4].w);
+    const int x1a = c1.i0 - ox1, x1b = c1.i1 - ox1, x2a = c2.i0 - ox2, x2b = c2.i1 - ox2, x3a = c3.i0 - ox3, x3b = c3.i1 - ox3;
+    const int xz4a = cz4.i0 - oxz4, xz4b = cz4.i1 - oxz4;
+    int xc4[4], xc5[4];
+    float wx4[4], wx5[4];
+    {
+        int ib; float t;
+        cubCoord(4, ic, ib, t); catmullRomWeights(t, wx4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xc4[k] = max(0, min(ib - 2 + k, P.diffuse[4].w - 1)) - ox4;
+        cubCoord(5, ic, ib, t); catmullRomWeights(t, wx5);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xc5[k] = max(0, min(ib - 2 + k, P.diffuse[5].w - 1)) - ox5;
+    }
+    const int h4 = P.diffuse[4].h, h5 = P.diffuse[5].h;
 
-    // ---------------------------------------------------------------- per-column set-up
-    const int nDf = P.nDiffuse, nDz = P.nDepth;
-    int lvD[6], lvZ[5];
+    // horizontal interpolation of one staged texel row for this lane's column
+    auto hrow1 = [&](int r) { F3 A = rgbOf(S.d1[r][x1a]), B = rgbOf(S.d1[r][x1b]); return fma3(c1.f, B - A, A); };
+    auto hrow2 = [&](int r) { F3 A = rgbOf(S.d2[r][x2a]), B = rgbOf(S.d2[r][x2b]); return fma3(c2.f, B - A, A); };
+    auto hrow3 = [&](int r) { F3 A = rgbOf(S.d3[r][x3a]), B = rgbOf(S.d3[r][x3b]); return fma3(c3.f, B - A, A); };
+    auto zrow1 = [&](int r) { float A = u16ToFloat(S.z1[r][x1a]), B = u16ToFloat(S.z1[r][x1b]); return fmaf(c1.f, B - A, A); };
+    auto zrow2 = [&](int r) { float A = u16ToFloat(S.z2[r][x2a]), B = u16ToFloat(S.z2[r][x2b]); return fmaf(c2.f, B - A, A); };
+    auto zrow3 = [&](int r) { float A = u16ToFloat(S.z3[r][x3a]), B = u16ToFloat(S.z3[r][x3b]); return fmaf(c3.f, B - A, A); };
+    auto zrow4 = [&](int r) { float A = u16ToFloat(S.z4[r][xz4a]), B = u16ToFloat(S.z4[r][xz4b]); return fmaf(cz4.f, B - A, A); };
+    auto crow4 = [&](int ib, int k) {
+        const int r = max(0, min(ib - 2 + k, h4 - 1)) - oy4;
+        F3 v = rgbOf(S.d4[r][xc4[0]]) * wx4[0];
+        v = fma3(wx4[1], rgbOf(S.d4[r][xc4[1]]), v);
+        v = fma3(wx4[2], rgbOf(S.d4[r][xc4[2]]), v);
+        return fma3(wx4[3], rgbOf(S.d4[r][xc4[3]]), v);
+    };
+    auto crow5 = [&](int ib, int k) {
+        const int r = max(0, min(ib - 2 + k, h5 - 1)) - oy5;
+        F3 v = rgbOf(S.d5[r][xc5[0]]) * wx5[0];
+        v = fma3(wx5[1], rgbOf(S.d5[r][xc5[1]]), v);
+        v = fma3(wx5[2], rgbOf(S.d5[r][xc5[2]]), v);
+        return fma3(wx5[3], rgbOf(S.d5[r][xc5[3]]), v);
+    };
+
+    // rolling state: bilinear levels keep (row A, row B - row A); bicubic levels keep their four rows
+    int rowA1 = -1, rowB1 = -1, rowA2 = -1, rowB2 = -1, rowA3 = -1, rowB3 = -1, rowA4 = -1, rowB4 = -1;
+    F3 a1{0, 0, 0}, d1 = a1, a2 = a1, d2 = a1, a3 = a1, d3 = a1;
+    float za1 = 0, zd1 = 0, za2 = 0, zd2 = 0, za3 = 0, zd3 = 0, za4 = 0, zd4 = 0;
+    int base4 = (int)0x80000000, base5 = base4;
+    F3 p4[4], p5[4];
 #pragma unroll
-    for (int l = 1; l <= 5; ++l) lvD[l] = min(l, nDf - 1);   // level clamp of linearSample / cubicSample
-#pragma unroll
-    for (int l = 1; l <= 4; ++l) lvZ[l] = min(l, nDz - 1);
-    XLin xD1 = xLinear(levelScale(lvD[1]), ic, P.diffuse[lvD[1]].w);
-    XLin xD2 = xLinear(levelScale(lvD[2]), ic, P.diffuse[lvD[2]].w);
-    XLin xD3 = xLinear(levelScale(lvD[3]), ic, P.diffuse[lvD[3]].w);
-    XCub xD4 = xCubic(levelScale(lvD[4]), ic, P.diffuse[lvD[4]].w);
-    XCub xD5 = xCubic(levelScale(lvD[5]), ic, P.diffuse[lvD[5]].w);
-    XLin xZ1 = xLinear(levelScale(lvZ[1]), ic, P.depth[lvZ[1]].w);
-    XLin xZ2 = xLinear(levelScale(lvZ[2]), ic, P.depth[lvZ[2]].w);
-    XLin xZ3 = xLinear(levelScale(lvZ[3]), ic, P.depth[lvZ[3]].w);
-    XLin xZ4 = xLinear(levelScale(lvZ[4]), ic, P.depth[lvZ[4]].w);
-    RollRGB rD1{-1, -1, {0, 0, 0}, {0, 0, 0}}, rD2 = rD1, rD3 = rD1;
-    RollCub rD4, rD5;
-    rD4.base = rD5.base = (int)0x80000000;
-    RollZ rZ1{-1, -1, 0.f, 0.f}, rZ2 = rZ1, rZ3 = rZ1, rZ4 = rZ1;
+    for (int k = 0; k < 4; ++k) p4[k] = p5[k] = a1;
+
+    const uint32_t mask = P.passMask;
+    const bool needMipsD = (mask & 0x40u) != 0, needMipsZ = (mask & 2u) != 0;
 
     // toEye.x and its square are column constants (legacypbr.d:756, 914) — exact sequence
     const float eyeX = __fsub_rn(0.5f, __fmul_rn((float)ic, P.invW));
@@ -284,28 +280,30 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_pbr_fast(const __grid_co
     const float nz2 = __fmul_rn(0.382658847856f, 0.382658847856f);
     const float multUshort = (float)(1.0 / 4655.0);
     const float kA = 0.00006510416f;  // 1/15360 as the reference's SIMD branch spells it (legacypbr.d:555)
-    const int noiseCol = (ic & 15) * 16;
+    const unsigned char* noisePtr = kBlueNoise16x16 + (ic & 15) * 16;
+    const float div255 = 1 / 255.0f;
 
     // sliding 3x3 depth window (raw values as float): rows j-1, j, j+1 at columns i-1, i, i+1
+    const int tx = ic - cx0;  // column of this lane inside the staged window (>= HALO_X)
     float zm[3], z0[3], zp[3];
-    {
-        const int r = box.miny - ry0;  // row of j = box.miny inside the window
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            // the staged window is clamped per element, so tx-1 / tx+1 are valid: tx >= HALO_X
-            zm[k] = tile[r - 1][tx - 1 + k];
-            z0[k] = tile[r][tx - 1 + k];
-        }
+    for (int k = 0; k < 3; ++k) {
+        zm[k] = S.depth[HALO_UP - 1][tx - 1 + k];
+        z0[k] = S.depth[HALO_UP][tx - 1 + k];
     }
 
-    for (int j = box.miny; j < box.maxy; ++j) {
-        const int r = j - ry0;
+    for (int j = box.miny; j <= yLast; ++j) {
+        const float* trow = &S.depth[j - ry0][tx];   // this lane's texel of row j inside the staged window
 #pragma unroll
-        for (int k = 0; k < 3; ++k) zp[k] = tile[r + 1][tx - 1 + k];
+        for (int k = 0; k < 3; ++k) zp[k] = trow[TILE_COLS - 1 + k];
+        const uint32_t diffusePx = diffuseNext, materialPx = materialNext;
+        {   // prefetch the next row's pixels (clamped on the last row: harmless re-read)
+            const int jn = min(j + 1, yLast);
+            diffuseNext = __ldg(rowPtr<uint32_t>(P.diffuse[0], jn) + ic);
+            materialNext = __ldg(rowPtr<uint32_t>(P.material, jn) + ic);
+        }
+        const RowSetup& rs = S.rows[j - box.miny];   // broadcast shared loads
 
-        const uint32_t diffusePx = __ldg(rowPtr<uint32_t>(P.diffuse[0], j) + ic);
-        const uint32_t materialPx = __ldg(rowPtr<uint32_t>(P.material, j) + ic);
-        const float div255 = 1 / 255.0f;
         const F3 base = rgbOf(diffusePx) * div255;
         const float rough = byteToFloat(materialPx, 0) * div255;
         const float metal = byteToFloat(materialPx, 1) * div255;
@@ -329,17 +327,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_pbr_fast(const __grid_co
             float m2 = __fadd_rn(__fmul_rn(d[2], c), __fmul_rn(d[7], e));
             float m3 = __fadd_rn(__fmul_rn(d[3], e), __fmul_rn(d[8], c));
             float filt = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[4], 0.38111009811f), m0), m1), m2), m3);
-            float a0 = __fsub_rn(d[0], filt), a1 = __fsub_rn(d[1], filt), a2 = __fsub_rn(d[2], filt), a3 = __fsub_rn(d[3], filt);
+            float a0 = __fsub_rn(d[0], filt), a1_ = __fsub_rn(d[1], filt), a2_ = __fsub_rn(d[2], filt), a3_ = __fsub_rn(d[3], filt);
             float b0 = __fsub_rn(d[5], filt), b1 = __fsub_rn(d[6], filt), b2 = __fsub_rn(d[7], filt), b3 = __fsub_rn(d[8], filt);
             // XZ weights (-c,0,c,-e | e,-c,0,c); YZ weights (-c,-e,-c,0 | 0,c,e,c).  A product with a zero
             // weight is +-0 and leaves its partner unchanged, so those adds are dropped.
             float xz0 = __fadd_rn(__fmul_rn(a0, -c), __fmul_rn(b0, e));
             float xz1 = __fmul_rn(b1, -c);
-            float xz2 = __fmul_rn(a2, c);
-            float xz3 = __fadd_rn(__fmul_rn(a3, -e), __fmul_rn(b3, c));
+            float xz2 = __fmul_rn(a2_, c);
+            float xz3 = __fadd_rn(__fmul_rn(a3_, -e), __fmul_rn(b3, c));
             float yz0 = __fmul_rn(a0, -c);
-            float yz1 = __fadd_rn(__fmul_rn(a1, -e), __fmul_rn(b1, c));
-            float yz2 = __fadd_rn(__fmul_rn(a2, -c), __fmul_rn(b2, e));
+            float yz1 = __fadd_rn(__fmul_rn(a1_, -e), __fmul_rn(b1, c));
+            float yz2 = __fadd_rn(__fmul_rn(a2_, -c), __fmul_rn(b2, e));
             float yz3 = __fmul_rn(b3, c);
             float xz = __fadd_rn(__fadd_rn(__fadd_rn(xz0, xz1), xz2), xz3);
             float yz = __fadd_rn(__fadd_rn(__fadd_rn(yz0, yz1), yz2), yz3);
@@ -357,12 +355,25 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_pbr_fast(const __grid_co
         const float zc = z0[1];
         F3 accum{0, 0, 0};
 
-        // ---- PassAmbientOcclusion (legacypbr.d:400-444)
-        if (mask & 2u) {
-            float s = sampleRollZ(rZ1, P.depth[lvZ[1]], xZ1, yLinear(lvZ[1], j, P.depth[lvZ[1]].h));
-            s += sampleRollZ(rZ2, P.depth[lvZ[2]], xZ2, yLinear(lvZ[2], j, P.depth[lvZ[2]].h));
-            s += sampleRollZ(rZ3, P.depth[lvZ[3]], xZ3, yLinear(lvZ[3], j, P.depth[lvZ[3]].h));
-            s += sampleRollZ(rZ4, P.depth[lvZ[4]], xZ4, yLinear(lvZ[4], j, P.depth[lvZ[4]].h));
+        // ---- PassAmbientOcclusion (legacypbr.d:400-444): depth levels 1..4, bilinear
+        if (needMipsZ) {
+            if (rs.iy[0] != rowA1 || rs.iy1[0] != rowB1) {
+                float na = zrow1(rs.iy[0]), nb = zrow1(rs.iy1[0]);
+                za1 = na; zd1 = nb - na;
+            }
+            if (rs.iy[1] != rowA2 || rs.iy1[1] != rowB2) {
+                float na = zrow2(rs.iy[1]), nb = zrow2(rs.iy1[1]);
+                za2 = na; zd2 = nb - na;
+            }
+            if (rs.iy[2] != rowA3 || rs.iy1[2] != rowB3) {
+                float na = zrow3(rs.iy[2]), nb = zrow3(rs.iy1[2]);
+                za3 = na; zd3 = nb - na;
+            }
+            if (rs.iy[3] != rowA4 || rs.iy1[3] != rowB4) {
+                float na = zrow4(rs.iy[3]), nb = zrow4(rs.iy1[3]);
+                za4 = na; zd4 = nb - na;
+            }
+            float s = fmaf(rs.fy[0], zd1, za1) + fmaf(rs.fy[1], zd2, za2) + fmaf(rs.fy[2], zd3, za3) + fmaf(rs.fy[3], zd4, za4);
             float diff = fmaf(s, -0.25f, zc);
             float cavity = fmaSat(diff, 1.0f / 23040, 1.0f);
             accum = base * (cavity * P.ambient);
@@ -371,15 +382,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_pbr_fast(const __grid_co
         // ---- PassObliqueShadowLight (legacypbr.d:460-616): clamp(1 + (z + s - d)/15360, 0, 1) per tap
         if (mask & 4u) {
             float lightL = 0.f, lightR = 0.f;
+            const float k0 = fmaf(zc, kA, 1.0f);
 #pragma unroll
             for (int s = 1; s <= 10; ++s) {
-                // columns are clamped in the staged window only at the image border; inside the image the
-                // window is wide enough (HALO_X), at the border the reference clamps too (legacypbr.d:532-534)
-                const int x1 = min(ic + s, W - 1) - cx0, x2 = max(ic - s, 0) - cx0;
-                const float ks = fmaf(zc + (float)s, kA, 1.0f);
-                const float* row = tile[r - s];
-                float c1 = fmaSat(row[x1], -kA, ks);
-                float c2 = fmaSat(row[x2], -kA, ks);
+                // the staged window is clamp-filled, so the taps (i +- s, j - s) (legacypbr.d:525-534, 568-576)
+                // sit at compile-time offsets from this lane's texel
+                const float ks = fmaf((float)s, kA, k0);
+                float c1 = fmaSat(trow[-s * TILE_COLS + s], -kA, ks);
+                float c2 = fmaSat(trow[-s * TILE_COLS - s], -kA, ks);
                 lightR = fmaf(c1, P.shadowW[s], lightR);
                 lightL = fmaf(c2, P.shadowW[s], lightL);
             }
@@ -412,7 +422,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_pbr_fast(const __grid_co
         // ---- PassSpecularLight (legacypbr.d:720-813)
         if (mask & 0x10u) {
             float hx = __fsub_rn(ex, -P.light3Dir[0]), hy = __fsub_rn(ey, -P.light3Dir[1]), hz = __fsub_rn(ez, -P.light3Dir[2]);
-            float inv = rsqrtss_x86(P.rsqrtTab, rsqrtArgExact(hx, hy, hz));
+            float hl2 = __fadd_rn(__fadd_rn(__fmul_rn(hx, hx), __fmul_rn(hy, hy)), __fmul_rn(hz, hz));
+            float inv = rsqrtss_x86(P.rsqrtTab, hl2);
             float sf = fmaf(hz * inv, nzc, fmaf(hy * inv, ny, (hx * inv) * nx));
             sf = fmaxf(sf, 1e-3f);
             float exponent = __ldg(P.expTab + roughByte);
@@ -437,10 +448,33 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_pbr_fast(const __grid_co
             float skyy = fmaf(fmaf(ry, 0.5f, 0.5f), P.skyFY, 0.5f);
             int il = __float2int_rz(lod);               // linearMipmapSample, mipmap.d:149-160
             float fl = lod - (float)il;
-            F3 sky = skySample(P, il, skyx, skyy);
-            if (fl != 0.f) {
-                F3 sky1 = skySample(P, il + 1, skyx, skyy);
-                sky = fma3(fl, sky1 - sky, sky);
+            F3 sky;
+            {
+                const int level = max(0, min(il, P.nSky - 1));
+                const DevLevel& L = P.sky[level];
+                Bilin s = bilinSetup(levelScale(level), skyx, skyy, L.w, L.h);
+                const uint32_t* r0 = rowPtr<uint32_t>(L, s.iy);
+                const uint32_t* r1 = rowPtr<uint32_t>(L, s.iy1);
+                uint32_t ta = __ldg(r0 + s.ix), tb = __ldg(r0 + s.ix1), tc = __ldg(r1 + s.ix), td = __ldg(r1 + s.ix1);
+                uint32_t ua = 0, ub = 0, uc = 0, ud = 0;
+                Bilin s2 = s;
+                if (fl != 0.f) {  // second level of the trilinear blend: issue its loads before using the first
+                    const int level2 = max(0, min(il + 1, P.nSky - 1));
+                    const DevLevel& L2 = P.sky[level2];
+                    s2 = bilinSetup(levelScale(level2), skyx, skyy, L2.w, L2.h);
+                    const uint32_t* q0 = rowPtr<uint32_t>(L2, s2.iy);
+                    const uint32_t* q1 = rowPtr<uint32_t>(L2, s2.iy1);
+                    ua = __ldg(q0 + s2.ix); ub = __ldg(q0 + s2.ix1); uc = __ldg(q1 + s2.ix); ud = __ldg(q1 + s2.ix1);
+                }
+                F3 A = rgbOf(ta), B = rgbOf(tb), C = rgbOf(tc), D = rgbOf(td);
+                F3 up = fma3(s.fx, B - A, A), down = fma3(s.fx, D - C, C);
+                sky = fma3(s.fy, down - up, up);
+                if (fl != 0.f) {
+                    F3 A2 = rgbOf(ua), B2 = rgbOf(ub), C2 = rgbOf(uc), D2 = rgbOf(ud);
+                    F3 up2 = fma3(s2.fx, B2 - A2, A2), down2 = fma3(s2.fx, D2 - C2, C2);
+                    F3 sky1 = fma3(s2.fy, down2 - up2, up2);
+                    sky = fma3(fl, sky1 - sky, sky);
+                }
             }
             float k = metal * (P.skyAmount * div255);
             accum.x = fmaf(base.x * sky.x, k, accum.x);
@@ -448,20 +482,56 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_pbr_fast(const __grid_co
             accum.z = fmaf(base.z * sky.z, k, accum.z);
         }
 
-        // ---- PassEmissiveContribution (legacypbr.d:948-1007, non-legacy branch)
-        if (mask & 0x40u) {
-            F3 s = sampleRollRGB(rD1, P.diffuse[lvD[1]], xD1, yLinear(lvD[1], j, P.diffuse[lvD[1]].h));
-            s = s + sampleRollRGB(rD2, P.diffuse[lvD[2]], xD2, yLinear(lvD[2], j, P.diffuse[lvD[2]].h));
-            s = s + sampleRollRGB(rD3, P.diffuse[lvD[3]], xD3, yLinear(lvD[3], j, P.diffuse[lvD[3]].h));
-            s = s + sampleRollCub(rD4, P.diffuse[lvD[4]], xD4, lvD[4], j);
-            F3 c5 = sampleRollCub(rD5, P.diffuse[lvD[5]], xD5, lvD[5], j);
-            float noise = (u16ToFloat(kBlueNoise16x16[noiseCol + (j & 15)]) - 127.5f) * 0.003f;
+        // ---- PassEmissiveContribution (legacypbr.d:948-1007, non-legacy branch): diffuse levels 1..3 bilinear,
+        // 4 and 5 bicubic
+        if (needMipsD) {
+            if (rs.iy[0] != rowA1 || rs.iy1[0] != rowB1) {   // warp-uniform
+                F3 na = (rs.iy[0] == rowB1) ? (a1 + d1) : hrow1(rs.iy[0]);
+                F3 nb = (rs.iy1[0] == rs.iy[0]) ? na : hrow1(rs.iy1[0]);
+                a1 = na; d1 = nb - na;
+            }
+            if (rs.iy[1] != rowA2 || rs.iy1[1] != rowB2) {
+                F3 na = (rs.iy[1] == rowB2) ? (a2 + d2) : hrow2(rs.iy[1]);
+                F3 nb = (rs.iy1[1] == rs.iy[1]) ? na : hrow2(rs.iy1[1]);
+                a2 = na; d2 = nb - na;
+            }
+            if (rs.iy[2] != rowA3 || rs.iy1[2] != rowB3) {
+                F3 na = (rs.iy[2] == rowB3) ? (a3 + d3) : hrow3(rs.iy[2]);
+                F3 nb = (rs.iy1[2] == rs.iy[2]) ? na : hrow3(rs.iy1[2]);
+                a3 = na; d3 = nb - na;
+            }
+            if (rs.ib4 != base4) {
+                if (rs.ib4 == base4 + 1) { p4[0] = p4[1]; p4[1] = p4[2]; p4[2] = p4[3]; p4[3] = crow4(rs.ib4, 3); }
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) p4[k] = crow4(rs.ib4, k);
+                }
+                base4 = rs.ib4;
+            }
+            if (rs.ib5 != base5) {
+                if (rs.ib5 == base5 + 1) { p5[0] = p5[1]; p5[1] = p5[2]; p5[2] = p5[3]; p5[3] = crow5(rs.ib5, 3); }
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) p5[k] = crow5(rs.ib5, k);
+                }
+                base5 = rs.ib5;
+            }
+            F3 s = fma3(rs.fy[0], d1, a1) + fma3(rs.fy[1], d2, a2) + fma3(rs.fy[2], d3, a3);
+            F3 c4 = fma3(rs.wy4[3], p4[3], fma3(rs.wy4[2], p4[2], fma3(rs.wy4[1], p4[1], p4[0] * rs.wy4[0])));
+            F3 c5 = fma3(rs.wy5[3], p5[3], fma3(rs.wy5[2], p5[2], fma3(rs.wy5[1], p5[1], p5[0] * rs.wy5[0])));
+            // clamp_0_to_65535 (mipmap.d:250-261); 8-bit sources cannot reach the upper bound
+            s = s + F3{fmaxf(c4.x, 0.f), fmaxf(c4.y, 0.f), fmaxf(c4.z, 0.f)};
+            c5 = F3{fmaxf(c5.x, 0.f), fmaxf(c5.y, 0.f), fmaxf(c5.z, 0.f)};
+            float noise = (u16ToFloat(__ldg(noisePtr + (j & 15))) - 127.5f) * 0.003f;
             const float AMT = 0.002f * 0.67f;
             float k5 = AMT * (1.0f + noise);
             accum.x = fmaf(c5.x, k5, fmaf(s.x, AMT, accum.x));
             accum.y = fmaf(c5.y, k5, fmaf(s.y, AMT, accum.y));
             accum.z = fmaf(c5.z, k5, fmaf(s.z, AMT, accum.z));
         }
+        // the depth and diffuse pyramids share the row bookkeeping of levels 1..3
+        rowA1 = rs.iy[0]; rowB1 = rs.iy1[0]; rowA2 = rs.iy[1]; rowB2 = rs.iy1[1];
+        rowA3 = rs.iy[2]; rowB3 = rs.iy1[2]; rowA4 = rs.iy[3]; rowB4 = rs.iy1[3];
 
         // ---- PassClampAndConvertTo8bit (legacypbr.d:1057-1107, non-legacy branch)
         if ((mask & 0x80u) && active) {
@@ -481,10 +551,19 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_pbr_fast(const __grid_co
 
 int pbr_fast_strip_rows() { return STRIP_ROWS; }
 
+static bool g_attrSet[64];
 void launch_pbr_fast(const PbrArgs& args, cudaStream_t stream) {
     const int grid = (args.nBoxes + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    if (args.nSky > 0) k_pbr_fast<true><<<grid, WARPS_PER_CTA * 32, 0, stream>>>(args);
-    else k_pbr_fast<false><<<grid, WARPS_PER_CTA * 32, 0, stream>>>(args);
+    const size_t smem = sizeof(WarpSmem) * WARPS_PER_CTA;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !g_attrSet[dev]) {  // > 48 KB of dynamic shared memory is an opt-in, per device
+        cudaFuncSetAttribute(k_pbr_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pbr_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        g_attrSet[dev] = true;
+    }
+    if (args.nSky > 0) k_pbr_fast<true><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(args);
+    else k_pbr_fast<false><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(args);
 }
 
 }  // namespace b2

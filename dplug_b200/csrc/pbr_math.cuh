@@ -29,15 +29,17 @@ static __device__ const unsigned char kBlueNoise16x16[256] = {  // gui/dplug/gui
 // x86 RSQRTSS as the reference executes it (gui/dplug/gui/ransac.d:43): a 2048-bin table indexed by
 // exponent parity and the top 10 mantissa bits, exact power-of-two scaling (see tools/gen_rsqrtss_table.c).
 __device__ __forceinline__ float rsqrtss_x86(const uint32_t* __restrict__ tab, float x) {
-    uint32_t b = __float_as_uint(x);
-    uint32_t e = b >> 23;  // sign bit included: negative operands give e >= 256
+    const uint32_t b = __float_as_uint(x);
+    const uint32_t e = b >> 23;  // sign bit included: negative operands give e >= 256
+    // normal positive operand: table entry of the bin, exponent shifted by floor((e - 126) / 2)
+    const int de = ((int)e - 126) >> 1;
+    float r = __uint_as_float(__ldg(tab + ((b >> 13) & 0x7ffu)) - ((uint32_t)de << 23));
     if (e - 1u >= 254u) {  // zero / denormal / inf / NaN / negative
-        if ((b << 1) > 0xff000000u) return x + x;
-        if (b & 0x80000000u) return __uint_as_float(((b & 0x7f800000u) == 0) ? 0xff800000u : 0xffc00000u);
-        return __uint_as_float(e == 0 ? 0x7f800000u : 0u);
+        if ((b << 1) > 0xff000000u) r = x + x;
+        else if (b & 0x80000000u) r = __uint_as_float(((b & 0x7f800000u) == 0) ? 0xff800000u : 0xffc00000u);
+        else r = __uint_as_float(e == 0 ? 0x7f800000u : 0u);
     }
-    int de = ((int)e - ((e & 1u) ? 127 : 126)) / 2;
-    return __uint_as_float(__ldg(tab + ((b >> 13) & 0x7ffu)) - ((uint32_t)de << 23));
+    return r;
 }
 
 // log_ps / exp_ps of sse_mathfun (the algorithm behind intel-intrinsics' _mm_pow_ps, which
