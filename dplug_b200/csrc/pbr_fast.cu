@@ -37,7 +37,7 @@ constexpr int TILE_COLS = 32 + 2 * HALO_X + 2; // +2: the staged window starts a
 constexpr int TILE_ROWS = STRIP_ROWS + HALO_UP + 1;
 constexpr int WARPS_PER_CTA = 4;
 #ifndef B2_MIN_CTAS
-#define B2_MIN_CTAS 3
+#define B2_MIN_CTAS 4
 #endif
 
 // window extents: a bilinear sampler of level l touches at most (32 >> l) + 2 texels along 32 pixels, a
@@ -55,7 +55,7 @@ static_assert(sizeof(RowSetup) % 16 == 0, "RowSetup is read with 128-bit shared 
 
 struct alignas(16) WarpSmem {
     RowSetup rows[STRIP_ROWS];
-    float depth[TILE_ROWS][TILE_COLS];
+    uint16_t depth[TILE_ROWS][TILE_COLS];   // raw L16; converted on use (keeps 4 CTAs / 16 warps per SM resident)
     uint32_t d1[W1][W1], d2[W2][W2], d3[W3][W3], d4[WC4][WC4], d5[WC5][WC5];
     uint16_t z1[W1][W1], z2[W2][W2], z3[W3][W3], z4[WZ4][WZ4];
 };
@@ -72,6 +72,13 @@ __device__ __forceinline__ float byteToFloat(uint32_t p, int k) {
     return __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7440 + k)) - 8388608.0f;
 }
 __device__ __forceinline__ F3 rgbOf(uint32_t p) { return F3{byteToFloat(p, 0), byteToFloat(p, 1), byteToFloat(p, 2)}; }
+// byte k -> float 32768 + b with a single PRMT (b lands in mantissa bits 8..15 of 2^15).  Used where a weighted
+// sum with weights adding up to 1 follows: the 32768 is subtracted once from the result (absolute error of the
+// intermediate sums <= 2^-8 of a 0..255 value, i.e. < 0.005 LSB after the sky / bloom scale factors)
+__device__ __forceinline__ float byteToFloatBiased(uint32_t p, int k) {
+    return __uint_as_float(__byte_perm(p, 0x47000000u, 0x7604 | (k << 4)));
+}
+__device__ __forceinline__ F3 rgbBiased(uint32_t p) { return F3{byteToFloatBiased(p, 0), byteToFloatBiased(p, 1), byteToFloatBiased(p, 2)}; }
 __device__ __forceinline__ float u16ToFloat(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
 
 __device__ __forceinline__ float fmaSat(float a, float b, float c) {
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
     const int ry0 = box.miny - HALO_UP;
     const int nRows = (box.maxy - box.miny) + HALO_UP + 1;
     if (2 * lane < TILE_COLS) {
-        const int c = 2 * lane;  // each lane converts a pair of texels per row
+        const int c = 2 * lane;  // each lane copies a pair of texels per row
         const int gx = cx0 + c;
         const bool pairOk = gx >= 0 && gx + 1 < W;
         const int gxa = max(0, min(gx, W - 1)), gxb = max(0, min(gx + 1, W - 1));
@@ -190,16 +197,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         for (int r = 0; r < nRows; ++r) {
             const int gy = max(0, min(ry0 + r, H - 1));
             const uint16_t* src = rowPtr<uint16_t>(D0, gy);
-            float f0, f1;
-            if (pairOk) {
-                uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + gx));
-                f0 = u16ToFloat(v & 0xffffu);
-                f1 = u16ToFloat(v >> 16);
-            } else {
-                f0 = u16ToFloat(__ldg(src + gxa));
-                f1 = u16ToFloat(__ldg(src + gxb));
-            }
-            *reinterpret_cast<float2*>(&S.depth[r][c]) = make_float2(f0, f1);
+            uint32_t v;
+            if (pairOk) v = __ldg(reinterpret_cast<const uint32_t*>(src + gx));
+            else v = (uint32_t)__ldg(src + gxa) | ((uint32_t)__ldg(src + gxb) << 16);
+            *reinterpret_cast<uint32_t*>(&S.depth[r][c]) = v;
         }
     }
 
@@ -283,19 +284,21 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
     const unsigned char* noisePtr = kBlueNoise16x16 + (ic & 15) * 16;
     const float div255 = 1 / 255.0f;
 
-    // sliding 3x3 depth window (raw values as float): rows j-1, j, j+1 at columns i-1, i, i+1
+    // sliding 3x3 window of d = depth * (1/FACTOR_Z) (legacypbr.d:304-314): rows j-1, j, j+1 at columns i-1, i, i+1
     const int tx = ic - cx0;  // column of this lane inside the staged window (>= HALO_X)
-    float zm[3], z0[3], zp[3];
+    float dm[3], d0[3], dp[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        zm[k] = S.depth[HALO_UP - 1][tx - 1 + k];
-        z0[k] = S.depth[HALO_UP][tx - 1 + k];
+        dm[k] = __fmul_rn(u16ToFloat(S.depth[HALO_UP - 1][tx - 1 + k]), multUshort);
+        d0[k] = __fmul_rn(u16ToFloat(S.depth[HALO_UP][tx - 1 + k]), multUshort);
     }
+    // shadow taps read the raw u16 as the float 2^23 + d (one LOP3, no subtraction): the bias is folded into ks
+    const float kBias = 8388608.0f * kA;
 
     for (int j = box.miny; j <= yLast; ++j) {
-        const float* trow = &S.depth[j - ry0][tx];   // this lane's texel of row j inside the staged window
+        const uint16_t* trow = &S.depth[j - ry0][tx];   // this lane's texel of row j inside the staged window
 #pragma unroll
-        for (int k = 0; k < 3; ++k) zp[k] = trow[TILE_COLS - 1 + k];
+        for (int k = 0; k < 3; ++k) dp[k] = __fmul_rn(u16ToFloat(trow[TILE_COLS - 1 + k]), multUshort);
         const uint32_t diffusePx = diffuseNext, materialPx = materialNext;
         {   // prefetch the next row's pixels (clamped on the last row: harmless re-read)
             const int jn = min(j + 1, yLast);
@@ -314,13 +317,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         // Exact reference sequence: the result feeds RSQRTSS.
         float nx = 0, ny = 0, nzc = 0, variance = 0;
         if (mask & 1u) {
-            float d[9];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                d[k] = __fmul_rn(zm[k], multUshort);
-                d[3 + k] = __fmul_rn(z0[k], multUshort);
-                d[6 + k] = __fmul_rn(zp[k], multUshort);
-            }
+            const float d[9] = {dm[0], dm[1], dm[2], d0[0], d0[1], d0[2], dp[0], dp[1], dp[2]};
             const float c = 0.03660694846f, e = 0.118115527008f;
             float m0 = __fadd_rn(__fmul_rn(d[0], c), __fmul_rn(d[5], e));
             float m1 = __fadd_rn(__fmul_rn(d[1], e), __fmul_rn(d[6], c));
@@ -345,15 +342,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
             float len2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), nz2);  // (+ w*w = +0 dropped)
             float inv = rsqrtss_x86(P.rsqrtTab, len2);
             nx = vx * inv; ny = vy * inv; nzc = 0.382658847856f * inv;
-            // variance (legacypbr.d:356-377): integer-valued floats, exact in any order
-            float ddx = (zm[0] + z0[0] + zp[0]) - 2.0f * (zm[1] + z0[1] + zp[1]) + (zm[2] + z0[2] + zp[2]);
-            float ddy = (zm[0] + zm[1] + zm[2]) - 2.0f * (z0[0] + z0[1] + z0[2]) + (zp[0] + zp[1] + zp[2]);
-            ddx *= (1 / 256.0f);
-            ddy *= (1 / 256.0f);
+            // variance (legacypbr.d:356-377): second differences of the 3x3 window.  The reference sums raw depths
+            // (exact); here they are rebuilt from d (relative error ~1e-7, the variance feeds no RSQRTSS)
+            float ddx = (d[0] + d[3] + d[6]) - 2.0f * (d[1] + d[4] + d[7]) + (d[2] + d[5] + d[8]);
+            float ddy = (d[0] + d[1] + d[2]) - 2.0f * (d[3] + d[4] + d[5]) + (d[6] + d[7] + d[8]);
+            const float kVar = 4655.0f / 256.0f;
+            ddx *= kVar;
+            ddy *= kVar;
             variance = fmaf(ddx, ddx, ddy * ddy);
         }
-        const float zc = z0[1];
-        F3 accum{0, 0, 0};
+        const float zc = u16ToFloat(trow[0]);
+        F3 T{0, 0, 0};   // light arriving per channel; every pass but the emissive one is base colour x light
 
         // ---- PassAmbientOcclusion (legacypbr.d:400-444): depth levels 1..4, bilinear
         if (needMipsZ) {
@@ -376,27 +375,28 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
             float s = fmaf(rs.fy[0], zd1, za1) + fmaf(rs.fy[1], zd2, za2) + fmaf(rs.fy[2], zd3, za3) + fmaf(rs.fy[3], zd4, za4);
             float diff = fmaf(s, -0.25f, zc);
             float cavity = fmaSat(diff, 1.0f / 23040, 1.0f);
-            accum = base * (cavity * P.ambient);
+            const float amb = cavity * P.ambient;
+            T = F3{amb, amb, amb};
         }
 
         // ---- PassObliqueShadowLight (legacypbr.d:460-616): clamp(1 + (z + s - d)/15360, 0, 1) per tap
         if (mask & 4u) {
             float lightL = 0.f, lightR = 0.f;
-            const float k0 = fmaf(zc, kA, 1.0f);
+            const float k0 = fmaf(zc, kA, 1.0f) + kBias;
 #pragma unroll
             for (int s = 1; s <= 10; ++s) {
                 // the staged window is clamp-filled, so the taps (i +- s, j - s) (legacypbr.d:525-534, 568-576)
                 // sit at compile-time offsets from this lane's texel
                 const float ks = fmaf((float)s, kA, k0);
-                float c1 = fmaSat(trow[-s * TILE_COLS + s], -kA, ks);
-                float c2 = fmaSat(trow[-s * TILE_COLS - s], -kA, ks);
+                float c1 = fmaSat(__uint_as_float(0x4B000000u | trow[-s * TILE_COLS + s]), -kA, ks);
+                float c2 = fmaSat(__uint_as_float(0x4B000000u | trow[-s * TILE_COLS - s]), -kA, ks);
                 lightR = fmaf(c1, P.shadowW[s], lightR);
                 lightL = fmaf(c2, P.shadowW[s], lightL);
             }
             float k = fmaf(lightL, 0.7f, lightR) * P.shadowInvTotal;
-            accum.x = fmaf(base.x * P.light1[0], k, accum.x);
-            accum.y = fmaf(base.y * P.light1[1], k, accum.y);
-            accum.z = fmaf(base.z * P.light1[2], k, accum.z);
+            T.x = fmaf(P.light1[0], k, T.x);
+            T.y = fmaf(P.light1[1], k, T.y);
+            T.z = fmaf(P.light1[2], k, T.z);
         }
 
         // ---- PassDirectionalLight (legacypbr.d:636-666)
@@ -405,9 +405,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
             float f = fmaf(0.5f, dot, 0.5f);
             float a = fmaf(rough, -0.5f, 0.24f);
             f = (f - a) * fastRcp(1.0f - a);  // linmap(f, a, 1, 0, 1), core/dplug/core/math.d:25-28
-            accum.x = fmaf(base.x * P.light2Col[0], f, accum.x);
-            accum.y = fmaf(base.y * P.light2Col[1], f, accum.y);
-            accum.z = fmaf(base.z * P.light2Col[2], f, accum.z);
+            T.x = fmaf(P.light2Col[0], f, T.x);
+            T.y = fmaf(P.light2Col[1], f, T.y);
+            T.z = fmaf(P.light2Col[2], f, T.z);
         }
 
         // toEye (legacypbr.d:756-757, 914-915): exact operand for RSQRTSS, shared by specular and skybox
@@ -433,9 +433,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
             float p = fastPow(sf, eF);
             float roughFactor = 10.0f * (1.0f - rough) * fmaf(metal, -0.5f, 1.0f);
             float k = p * roughFactor * tok * specAmt;
-            accum.x = fmaf(base.x * P.light3Col[0], k, accum.x);
-            accum.y = fmaf(base.y * P.light3Col[1], k, accum.y);
-            accum.z = fmaf(base.z * P.light3Col[2], k, accum.z);
+            T.x = fmaf(P.light3Col[0], k, T.x);
+            T.y = fmaf(P.light3Col[1], k, T.y);
+            T.z = fmaf(P.light3Col[2], k, T.z);
         }
 
         // ---- PassSkyboxReflections (legacypbr.d:872-930)
@@ -466,21 +466,24 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
                     const uint32_t* q1 = rowPtr<uint32_t>(L2, s2.iy1);
                     ua = __ldg(q0 + s2.ix); ub = __ldg(q0 + s2.ix1); uc = __ldg(q1 + s2.ix); ud = __ldg(q1 + s2.ix1);
                 }
-                F3 A = rgbOf(ta), B = rgbOf(tb), C = rgbOf(tc), D = rgbOf(td);
+                F3 A = rgbBiased(ta), B = rgbBiased(tb), C = rgbBiased(tc), D = rgbBiased(td);
                 F3 up = fma3(s.fx, B - A, A), down = fma3(s.fx, D - C, C);
                 sky = fma3(s.fy, down - up, up);
                 if (fl != 0.f) {
-                    F3 A2 = rgbOf(ua), B2 = rgbOf(ub), C2 = rgbOf(uc), D2 = rgbOf(ud);
+                    F3 A2 = rgbBiased(ua), B2 = rgbBiased(ub), C2 = rgbBiased(uc), D2 = rgbBiased(ud);
                     F3 up2 = fma3(s2.fx, B2 - A2, A2), down2 = fma3(s2.fx, D2 - C2, C2);
                     F3 sky1 = fma3(s2.fy, down2 - up2, up2);
                     sky = fma3(fl, sky1 - sky, sky);
                 }
+                sky = F3{sky.x - 32768.0f, sky.y - 32768.0f, sky.z - 32768.0f};
             }
             float k = metal * (P.skyAmount * div255);
-            accum.x = fmaf(base.x * sky.x, k, accum.x);
-            accum.y = fmaf(base.y * sky.y, k, accum.y);
-            accum.z = fmaf(base.z * sky.z, k, accum.z);
+            T.x = fmaf(sky.x, k, T.x);
+            T.y = fmaf(sky.y, k, T.y);
+            T.z = fmaf(sky.z, k, T.z);
         }
+
+        F3 accum{base.x * T.x, base.y * T.y, base.z * T.z};
 
         // ---- PassEmissiveContribution (legacypbr.d:948-1007, non-legacy branch): diffuse levels 1..3 bilinear,
         // 4 and 5 bicubic
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
 
         // slide the depth window down
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { zm[k] = z0[k]; z0[k] = zp[k]; }
+        for (int k = 0; k < 3; ++k) { dm[k] = d0[k]; d0[k] = dp[k]; }
     }
 }
 
