@@ -1,0 +1,136 @@
+/**
+ * CUDA drop-in for Dplug's PBR compositor: binds libb2pbr.so (include/b2pbr.h).
+ *
+ * NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no D toolchain (no dmd / ldc2 / gdc / dub).
+ * It depends only on declarations that exist in Dplug: ICompositor, CompositorCreationContext
+ * (gui/dplug/gui/compositor.d:29-76), Mipmap / OwnedImage / ImageRef (graphics/dplug/graphics/mipmap.d,
+ * image.d), box2i (math/dplug/math/box.d) and IProfiler (core/dplug/core/profiler.d).
+ *
+ * Install it by overriding GUIGraphics.buildCompositor (gui/dplug/gui/graphics.d:125-129):
+ *
+ *     override ICompositor buildCompositor(CompositorCreationContext* context)
+ *     {
+ *         return mallocNew!CudaPBRCompositor(context);
+ *     }
+ */
+module dplug.gui.cudacompositor;
+
+import dplug.core.nogc;
+import dplug.core.profiler;
+import dplug.math.box;
+import dplug.math.vector;
+import dplug.graphics;
+import dplug.gui.compositor;
+
+nothrow @nogc:
+
+// ---- include/b2pbr.h -------------------------------------------------------------------------------------
+extern(C) nothrow @nogc
+{
+    struct b2pbr;
+    struct b2mip;
+    struct b2_box2i { int min_x, min_y, max_x, max_y; }           // == box2i, math/dplug/math/box.d:29-30
+    struct b2_imageref { int w, h; size_t pitch; void* pixels; }   // == ImageRef!T, image.d:127-131
+    struct b2pbr_params
+    {
+        float[3] light1_color, light2_dir, light2_color, light3_dir, light3_color;
+        float ambient_light, skybox_amount, tonemap_threshold, tonemap_ratio;
+        uint pass_active_mask;
+    }
+    const(char)* b2_last_error();
+    int b2pbr_create(b2pbr** o, int device);
+    void b2pbr_destroy(b2pbr*);
+    int b2pbr_resize(b2pbr*, int width, int height, int areaMaxWidth, int areaMaxHeight);
+    int b2pbr_set_params(b2pbr*, const(b2pbr_params)*);
+    int b2pbr_get_params(const(b2pbr)*, b2pbr_params*);
+    void b2pbr_default_params(b2pbr_params*);
+    int b2pbr_set_skybox(b2pbr*, const(ubyte)* rgba, int w, int h, size_t pitch);
+    int b2pbr_composite_tile_host(b2pbr*, b2_imageref wfb, const(b2_box2i)* areas, int nAreas,
+                                  const(b2_box2i)* updateRects, int nUpdate,
+                                  b2_imageref diffuseL0, b2_imageref materialL0, b2_imageref depthL0);
+    int b2_host_register(void* ptr, size_t bytes);
+    int b2_host_unregister(void* ptr);
+}
+
+/// ICompositor backed by the B200 library.  Same calls, same arguments, same threading contract as
+/// PBRCompositor (gui/dplug/gui/legacypbr.d:67-266); the mip levels the passes sample are regenerated on
+/// the device from level 0, so the CPU-side levels GUIGraphics.regenerateMipmaps fills are simply not read
+/// (a GUIGraphics subclass may override regenerateMipmaps, graphics.d:1354, to skip that CPU work).
+final class CudaPBRCompositor : ICompositor
+{
+public:
+nothrow:
+@nogc:
+
+    this(CompositorCreationContext* context, int device = 0)
+    {
+        // context.threadPool is not used: tiles are scheduled over the GPU's SMs
+        int rc = b2pbr_create(&_h, device);
+        assert(rc == 0, "b2pbr_create failed (no CUDA device? this compositor has no CPU fallback)");
+        b2pbr_default_params(&_params);
+    }
+
+    ~this()
+    {
+        if (_h) b2pbr_destroy(_h);
+    }
+
+    /// compositor.d:43-46
+    override void resizeBuffers(int width, int height, int areaMaxWidth, int areaMaxHeight)
+    {
+        int rc = b2pbr_resize(_h, width, height, areaMaxWidth, areaMaxHeight);
+        assert(rc == 0);
+    }
+
+    /// compositor.d:63-68.  `areas` are the tiles of the PBR dirty rects grown by the update margin
+    /// (graphics.d:930-936), i.e. a superset of what changed in level 0: they are uploaded, the device
+    /// mips regenerated for them, the tiles composited and copied back into `wfb`.
+    override void compositeTile(ImageRef!RGBA wfb, const(box2i)[] areas,
+                                Mipmap!RGBA diffuseMap, Mipmap!RGBA materialMap, Mipmap!L16 depthMap,
+                                IProfiler profiler)
+    {
+        static b2_imageref toC(T)(OwnedImage!T img)
+        {
+            return b2_imageref(img.w, img.h, cast(size_t) img.pitchInBytes(), cast(void*) img.scanlinePtr(0));
+        }
+        b2_imageref out_ = b2_imageref(wfb.w, wfb.h, wfb.pitch, cast(void*) wfb.pixels);
+        static assert(box2i.sizeof == b2_box2i.sizeof);
+        int rc = b2pbr_composite_tile_host(_h, out_, cast(const(b2_box2i)*) areas.ptr, cast(int) areas.length,
+                                           null, 0,
+                                           toC(diffuseMap.levels[0]), toC(materialMap.levels[0]), toC(depthMap.levels[0]));
+        assert(rc == 0);
+    }
+
+    // <LEGACY> setters, legacypbr.d:75-123
+    void light1Color(vec3f c)   { _params.light1_color = [c.x, c.y, c.z]; push(); }
+    void light2Dir(vec3f d)     { _params.light2_dir   = [d.x, d.y, d.z]; push(); }
+    void light2Color(vec3f c)   { _params.light2_color = [c.x, c.y, c.z]; push(); }
+    void light3Dir(vec3f d)     { _params.light3_dir   = [d.x, d.y, d.z]; push(); }
+    void light3Color(vec3f c)   { _params.light3_color = [c.x, c.y, c.z]; push(); }
+    void skyboxAmount(float a)  { _params.skybox_amount = a; push(); }
+    void ambientLight(float a)  { _params.ambient_light = a; push(); }
+    void tonemapThreshold(float v) { _params.tonemap_threshold = v; push(); }
+    void tonemapRatio(float v)  { _params.tonemap_ratio = v; push(); }
+
+    /// getPass(n).setActive(active), compositor.d:170-173,222-225
+    void setPassActive(int pass, bool active)
+    {
+        if (active) _params.pass_active_mask |= (1u << pass);
+        else _params.pass_active_mask &= ~(1u << pass);
+        push();
+    }
+
+    /// PassSkyboxReflections.setSkybox (legacypbr.d:861-870): the pixels are copied to the device; like the
+    /// reference this call takes ownership of the image and frees it.
+    void setSkybox(OwnedImage!RGBA image)
+    {
+        int rc = b2pbr_set_skybox(_h, cast(const(ubyte)*) image.scanlinePtr(0), image.w, image.h, image.pitchInBytes());
+        assert(rc == 0);
+        image.destroyFree();
+    }
+
+private:
+    b2pbr* _h;
+    b2pbr_params _params;
+    void push() { int rc = b2pbr_set_params(_h, &_params); assert(rc == 0); }
+}
