@@ -172,6 +172,20 @@ class PBRCompositor:
             _lib.check(self._l.b2pbr_download_swizzled(self._h, pixelFormat, out.ctypes.data_as(C.c_void_p), out.strides[0], arr, len(rects)))
         return out
 
+    def downloadRows(self, row0, row1):
+        """rows [row0, row1) of the composited buffer (band objects hold only their own rows)"""
+        out = np.zeros((row1 - row0, self.width, 4), dtype=np.uint8)
+        if row1 > row0:
+            origin = out.ctypes.data - row0 * out.strides[0]
+            _lib.check(self._l.b2pbr_download(self._h, C.c_void_p(origin), out.strides[0], _lib.boxes([(0, row0, self.width, row1)]), 1))
+        return out
+
+    def bandRows(self, which, level=0):
+        """(stored_lo, stored_hi, need_lo, need_hi) rows of a pyramid level (see b2pbr_band_rows)."""
+        v = [C.c_int() for _ in range(4)]
+        _lib.check(self._l.b2pbr_band_rows(self._h, which, level, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
     def sync(self):
         _lib.check(self._l.b2pbr_sync(self._h))
 

@@ -341,6 +341,8 @@ struct b2pbr {
     int W = 0, H = 0, tileW = 64, tileH = 64;
     bool banded = false;
     int bandY0 = 0, bandY1 = 0;
+    // rows [lo, hi) of every pyramid level this band has to hold valid data for (banded objects only)
+    int needD[kMaxDiffuseLevels][2], needZ[kMaxDepthLevels][2];
     b2mip *diffuse = nullptr, *material = nullptr, *depth = nullptr, *sky = nullptr;
     DevLevel out{}; uint8_t* outAlloc = nullptr;
     DevLevel swz{}; uint8_t* swzAlloc = nullptr;
@@ -374,6 +376,84 @@ static void normalized3(float x, float y, float z, float out[3]) {  // vec3f.nor
     s += x * x; s += y * y; s += z * z;
     float inv = 1 / std::sqrt(s);
     out[0] = x * inv; out[1] = y * inv; out[2] = z * inv;
+}
+
+// ---- which rows of each level does a band [y0, y1) read?  (host replica of the samplers' row arithmetic)
+static void linRows(int l, int j, int h, int& r0, int& r1) {   // Mipmap.linearSample, mipmap.d:309-339
+    int n = 2 * j + 1 - (1 << l);
+    if (n < 0) n = 0;
+    r0 = n >> (l + 1);
+    if (r0 > h - 1) r0 = h - 1;
+    r1 = r0 + 1 > h - 1 ? h - 1 : r0 + 1;
+}
+static void cubRows(int l, int j, int h, int& r0, int& r1) {   // Mipmap.cubicSample, mipmap.d:182-193
+    int ib = (2 * j + 1 - (1 << l) + (2 << l)) >> (l + 1);
+    r0 = ib - 2 < 0 ? 0 : (ib - 2 > h - 1 ? h - 1 : ib - 2);
+    r1 = ib + 1 < 0 ? 0 : (ib + 1 > h - 1 ? h - 1 : ib + 1);
+}
+static void unite(int* need, int lo, int hi) {  // half-open [lo, hi)
+    if (need[0] == need[1]) { need[0] = lo; need[1] = hi; return; }
+    if (lo < need[0]) need[0] = lo;
+    if (hi > need[1]) need[1] = hi;
+}
+// rows of the previous level a generateLevel over dst rows [a, b) reads (mipmap.d:683-686, 906-919)
+static void genSourceRows(bool cubic, int a, int b, int hs, int& lo, int& hi) {
+    if (cubic) { lo = 2 * a - 1 < 0 ? 0 : 2 * a - 1; hi = (2 * (b - 1) + 2 > hs - 1 ? hs - 1 : 2 * (b - 1) + 2) + 1; }
+    else { lo = 2 * a; hi = 2 * (b - 1) + 2; }
+}
+// Pure host arithmetic (no device): rows [lo, hi) of every level a band [y0, y1) of a W x H canvas must hold.
+static void computeBandNeeds(int W, int H, int y0, int y1, int needD[kMaxDiffuseLevels][2], int needZ[kMaxDepthLevels][2]) {
+    const int nD = countLevels(5, W, H), nZ = countLevels(4, W, H);   // graphics.d:1118-1119
+    for (int l = 0; l < kMaxDiffuseLevels; ++l) needD[l][0] = needD[l][1] = 0;
+    for (int l = 0; l < kMaxDepthLevels; ++l) needZ[l][0] = needZ[l][1] = 0;
+    if (y1 <= y0 || nD == 0) return;
+    int a, b, e, f;
+    // what the passes sample (level clamp: levels beyond the pyramid read the last one)
+    for (int l = 1; l <= 5; ++l) {
+        const int lv = l < nD ? l : nD - 1;
+        if (lv == 0) continue;
+        const int h = H >> lv;
+        if (l <= 3) { linRows(lv, y0, h, a, b); linRows(lv, y1 - 1, h, e, f); }
+        else { cubRows(lv, y0, h, a, b); cubRows(lv, y1 - 1, h, e, f); }
+        unite(needD[lv], a, f + 1);
+    }
+    for (int l = 1; l <= 4; ++l) {
+        const int lv = l < nZ ? l : nZ - 1;
+        if (lv == 0) continue;
+        const int h = H >> lv;
+        linRows(lv, y0, h, a, b); linRows(lv, y1 - 1, h, e, f);
+        unite(needZ[lv], a, f + 1);
+    }
+    // level 0: own rows, the shadow reach (10 rows up) and the normal stencil (1 row each way)
+    unite(needD[0], y0, y1);
+    unite(needZ[0], y0 - 10 < 0 ? 0 : y0 - 10, y1 + 1 > H ? H : y1 + 1);
+    // what generating those rows reads, top level first
+    for (int l = nD - 1; l >= 1; --l) {
+        if (needD[l][0] == needD[l][1]) continue;
+        int lo, hi;
+        genSourceRows(l >= 2, needD[l][0], needD[l][1], H >> (l - 1), lo, hi);  // graphics.d:1380-1384
+        unite(needD[l - 1], lo, hi);
+    }
+    for (int l = nZ - 1; l >= 1; --l) {
+        if (needZ[l][0] == needZ[l][1]) continue;
+        int lo, hi;
+        genSourceRows(l >= 3, needZ[l][0], needZ[l][1], H >> (l - 1), lo, hi);   // graphics.d:1414
+        unite(needZ[l - 1], lo, hi);
+    }
+}
+
+static int pbrBandNeeds(b2pbr* c) {
+    computeBandNeeds(c->W, c->H, c->bandY0, c->bandY1, c->needD, c->needZ);
+    // the band objects must store all of it
+    for (int l = 0; l < (int)c->diffuse->levels.size(); ++l) {
+        const DevLevel& L = c->diffuse->levels[l];
+        if (c->needD[l][0] < L.y0 || c->needD[l][1] > L.y0 + L.rows) return fail(B2_ERR_STATE, "band: diffuse halo too small");
+    }
+    for (int l = 0; l < (int)c->depth->levels.size(); ++l) {
+        const DevLevel& L = c->depth->levels[l];
+        if (c->needZ[l][0] < L.y0 || c->needZ[l][1] > L.y0 + L.rows) return fail(B2_ERR_STATE, "band: depth halo too small");
+    }
+    return B2_OK;
 }
 
 static void pbrFreeMaps(b2pbr* c) {
@@ -602,6 +682,7 @@ int b2pbr_resize(b2pbr* c, int width, int height, int tw, int th) {
     c->swz = c->out;
     CU(cudaMalloc((void**)&c->swzAlloc, (size_t)c->out.pitch * (size_t)(c->out.rows > 0 ? c->out.rows : 1)));
     c->swz.base = c->swzAlloc;
+    if (c->banded) return pbrBandNeeds(c);
     return B2_OK;
 }
 
@@ -666,7 +747,14 @@ int b2pbr_regenerate_mipmaps(b2pbr* c, const b2_box2i* rects, int n) {
     for (int level = 1; level < (int)c->diffuse->levels.size(); ++level) {
         int q = level == 1 ? B2_QUALITY_BOX_ALPHACOV_PREMUL : B2_QUALITY_CUBIC;  // graphics.d:1380-1384
         for (auto& area : s0) {
-            int rc = b2mip_generate_next_level(c->diffuse, q, area, level, &area);
+            const DevLevel& Pv = c->diffuse->levels[level - 1];
+            area = impactOnNextLevel(q, area, Pv.w, Pv.h);
+            b2_box2i r = area;
+            if (c->banded) {  // a band only regenerates the rows it reads (its neighbours own the others)
+                if (r.min_y < c->needD[level][0]) r.min_y = c->needD[level][0];
+                if (r.max_y > c->needD[level][1]) r.max_y = c->needD[level][1];
+            }
+            int rc = mipGenerateLevel(c->diffuse, level, q, r);
             if (rc) return rc;
         }
     }
@@ -676,7 +764,14 @@ int b2pbr_regenerate_mipmaps(b2pbr* c, const b2_box2i* rects, int n) {
     for (int level = 1; level < (int)c->depth->levels.size(); ++level) {
         int q = level >= 3 ? B2_QUALITY_CUBIC : B2_QUALITY_BOX;  // graphics.d:1414
         for (auto& area : s1) {
-            int rc = b2mip_generate_next_level(c->depth, q, area, level, &area);
+            const DevLevel& Pv = c->depth->levels[level - 1];
+            area = impactOnNextLevel(q, area, Pv.w, Pv.h);
+            b2_box2i r = area;
+            if (c->banded) {
+                if (r.min_y < c->needZ[level][0]) r.min_y = c->needZ[level][0];
+                if (r.max_y > c->needZ[level][1]) r.max_y = c->needZ[level][1];
+            }
+            int rc = mipGenerateLevel(c->depth, level, q, r);
             if (rc) return rc;
         }
     }
@@ -762,6 +857,38 @@ int b2pbr_composite_tile_host(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, 
     rc = b2pbr_download(c, wfb.pixels, wfb.pitch, areas, n_areas);
     traceEnd(c);
     return rc;
+}
+
+int b2_band_need_rows(int W, int H, int y0, int y1, int map, int level, int* need_lo, int* need_hi) {
+    if (W <= 0 || H <= 0 || y0 < 0 || y1 > H || y0 > y1 || level < 0) return fail(B2_ERR_INVALID, "band_need_rows: bad arguments");
+    int nd[kMaxDiffuseLevels][2], nz[kMaxDepthLevels][2];
+    computeBandNeeds(W, H, y0, y1, nd, nz);
+    int lo, hi;
+    if (map == B2_MAP_DIFFUSE && level < kMaxDiffuseLevels) { lo = nd[level][0]; hi = nd[level][1]; }
+    else if (map == B2_MAP_DEPTH && level < kMaxDepthLevels) { lo = nz[level][0]; hi = nz[level][1]; }
+    else if (map == B2_MAP_MATERIAL && level == 0) { lo = y0; hi = y1; }
+    else return fail(B2_ERR_INVALID, "band_need_rows: bad map / level");
+    if (need_lo) *need_lo = lo;
+    if (need_hi) *need_hi = hi;
+    return B2_OK;
+}
+
+int b2pbr_band_rows(const b2pbr* c, int map, int level, int* stored_lo, int* stored_hi, int* need_lo, int* need_hi) {
+    if (!c || !c->diffuse) return fail(B2_ERR_STATE, "band_rows before resize");
+    const b2mip* m = map == B2_MAP_DIFFUSE ? c->diffuse : (map == B2_MAP_DEPTH ? c->depth : (map == B2_MAP_MATERIAL ? c->material : nullptr));
+    if (!m || level < 0 || level >= (int)m->levels.size()) return fail(B2_ERR_INVALID, "band_rows: bad map / level");
+    const DevLevel& L = m->levels[level];
+    if (stored_lo) *stored_lo = L.y0;
+    if (stored_hi) *stored_hi = L.y0 + L.rows;
+    int lo = L.y0, hi = L.y0 + L.rows;
+    if (c->banded) {
+        if (map == B2_MAP_DIFFUSE) { lo = c->needD[level][0]; hi = c->needD[level][1]; }
+        else if (map == B2_MAP_DEPTH) { lo = c->needZ[level][0]; hi = c->needZ[level][1]; }
+        else { lo = c->bandY0; hi = c->bandY1; }
+    }
+    if (need_lo) *need_lo = lo;
+    if (need_hi) *need_hi = hi;
+    return B2_OK;
 }
 
 int b2pbr_sync(b2pbr* c) {

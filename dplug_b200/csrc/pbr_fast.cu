@@ -489,18 +489,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         // 4 and 5 bicubic
         if (needMipsD) {
             if (rs.iy[0] != rowA1 || rs.iy1[0] != rowB1) {   // warp-uniform
-                F3 na = (rs.iy[0] == rowB1) ? (a1 + d1) : hrow1(rs.iy[0]);
-                F3 nb = (rs.iy1[0] == rs.iy[0]) ? na : hrow1(rs.iy1[0]);
+                F3 na = hrow1(rs.iy[0]), nb = hrow1(rs.iy1[0]);   // both rows: results independent of the strip cut
                 a1 = na; d1 = nb - na;
             }
             if (rs.iy[1] != rowA2 || rs.iy1[1] != rowB2) {
-                F3 na = (rs.iy[1] == rowB2) ? (a2 + d2) : hrow2(rs.iy[1]);
-                F3 nb = (rs.iy1[1] == rs.iy[1]) ? na : hrow2(rs.iy1[1]);
+                F3 na = hrow2(rs.iy[1]), nb = hrow2(rs.iy1[1]);   // both rows: results independent of the strip cut
                 a2 = na; d2 = nb - na;
             }
             if (rs.iy[2] != rowA3 || rs.iy1[2] != rowB3) {
-                F3 na = (rs.iy[2] == rowB3) ? (a3 + d3) : hrow3(rs.iy[2]);
-                F3 nb = (rs.iy1[2] == rs.iy[2]) ? na : hrow3(rs.iy1[2]);
+                F3 na = hrow3(rs.iy[2]), nb = hrow3(rs.iy1[2]);   // both rows: results independent of the strip cut
                 a3 = na; d3 = nb - na;
             }
             if (rs.ib4 != base4) {

@@ -82,6 +82,25 @@ class Mipmap:
         _lib.check(self._l.b2mip_upload(self._h, level, image.ctypes.data_as(C.c_void_p), pitch, _lib.boxes(rects), len(rects)))
         _lib.check(self._l.b2mip_sync(self._h))  # the numpy temporary may go away
 
+    def uploadRows(self, level, rows, row0, x0=0):
+        """host -> device for a block of rows: `rows[k]` is global row `row0 + k` of the level (band objects)."""
+        rows = np.ascontiguousarray(rows, dtype=self._dtype())
+        n, w = rows.shape[0], rows.shape[1]
+        if n == 0:
+            return
+        pitch = rows.strides[0]
+        origin = rows.ctypes.data - row0 * pitch - x0 * (4 if self.color == RGBA8 else 2)   # address of global pixel (0, 0)
+        _lib.check(self._l.b2mip_upload(self._h, level, C.c_void_p(origin), pitch, _lib.boxes([(x0, row0, x0 + w, row0 + n)]), 1))
+        _lib.check(self._l.b2mip_sync(self._h))
+
+    def downloadRows(self, level, row0, row1):
+        w, h, _, _, _ = self.levelInfo(level)
+        out = np.zeros((row1 - row0, w, 4) if self.color == RGBA8 else (row1 - row0, w), dtype=self._dtype())
+        if row1 > row0:
+            origin = out.ctypes.data - row0 * out.strides[0]
+            _lib.check(self._l.b2mip_download(self._h, level, C.c_void_p(origin), out.strides[0], _lib.boxes([(0, row0, w, row1)]), 1))
+        return out
+
     def download(self, level, rects=None, out=None):
         shape = self._shape(level)
         if out is None:

@@ -179,6 +179,12 @@ int b2pbr_download(b2pbr*, void* host, size_t host_pitch, const b2_box2i* rects,
 /* fused post-composite step (graphics.d:1425-1452,1527-1654 reorderComponents): same download but
  * swizzled to the window's pixel order with alpha forced to 255 */
 int b2pbr_download_swizzled(b2pbr*, int pixel_format, void* host, size_t host_pitch, const b2_box2i* rects, int n);
+/* Row ranges [lo, hi) of one pyramid level: `stored_*` = rows this object holds, `need_*` = rows it must hold
+ * VALID data for before compositing its band (for level 0 of a banded object these are the rows to fill by
+ * upload + halo exchange with the neighbouring bands).  Unbanded: the whole level. */
+/* the same "need" rows as pure host arithmetic (no device, no object): used to plan the halo exchange */
+int b2_band_need_rows(int W, int H, int y0, int y1, int map, int level, int* need_lo, int* need_hi);
+int b2pbr_band_rows(const b2pbr*, int map, int level, int* stored_lo, int* stored_hi, int* need_lo, int* need_hi);
 int b2pbr_sync(b2pbr*);
 
 /* SimpleRawCompositor (compositor.d:260-298): copy diffuse RGB, alpha = 255, into the composited twin */
