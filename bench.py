@@ -22,6 +22,8 @@ WORKLOADS = {
     # name: (W, H, description)
     "c1": (620, 330, "C1 examples/distort default size 620x330, full-frame composite"),
     "c2": (3840, 2160, "C2 synthetic 3840x2160 diffuse/material/depth, full re-composite"),
+    "c3": (8192, 8192, "C3 emissive Mipmap bloom pyramid (generateNextLevel, 8 levels) on 8192x8192 RGBA"),
+    "c5": (16384, 16384, "C5 16384x16384 single canvas row-banded over the GPUs, level-0 halo exchange per frame"),
 }
 
 
@@ -289,6 +291,149 @@ def run_b200(args, W, H, desc):
         dist.destroy_process_group()
 
 
+class _DevView:
+    """zero-copy view of device memory for torch (cuda array interface)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2, "strides": None}
+
+
+def _peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def run_c3(args, W, H, desc):
+    """BASELINE config 3: the diffuse (emissive) pyramid recipe on one 8192x8192 RGBA image: level 1
+    boxAlphaCovIntoPremul, levels 2..8 cubic (graphics.d:1378-1392 with Mipmap(8))."""
+    import numpy as np
+    import torch
+    import dplug_b200 as b2
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream()
+    R = 2   # two images (2 x 358 MB) alternate so the source is not L2-resident
+    rng = np.random.default_rng(1)
+    base = rng.integers(0, 256, size=(H // 8, W, 4), dtype=np.uint8)
+    mips = []
+    for k in range(R):
+        m = b2.Mipmap(b2.RGBA8, 8, W, H)
+        m.set_stream(stream.cuda_stream)
+        for b in range(8):
+            m.uploadRows(0, np.roll(base, k * 7 + b, axis=0), b * (H // 8))
+        mips.append(m)
+    for i in range(max(3, args.warmup)):
+        mips[i % R].generateChain(2, 2)
+    torch.cuda.synchronize()
+    l0 = sum(m.kernelLaunches() for m in mips)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(0); sampler.start(); time.sleep(0.3)
+    e0.record(stream)
+    for i in range(args.steps):
+        mips[i % R].generateChain(2, 2)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    B = 4 * W * H + 4 * sum((W >> l) * (H >> l) for l in range(1, 9))
+    peak, src = _peak()
+    achieved = B * args.steps / (ms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "pyramid L0-Mpix/s (8-level emissive Mipmap chain)", "value": W * H * args.steps / (ms * 1e-3) / 1e6, "unit": "Mpix/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": desc, "l2": "inputs larger than L2: %d images alternate (%.0f MB each)" % (R, B / 1e6)},
+        "roofline": {"bound": "hbm", "kernel": "mip chain (k_box_rgba<premul> + 7 x k_cubic_rgba)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": src, "algorithmic_bytes_per_launch": B},
+        "gpu_launches": int(sum(m.kernelLaunches() for m in mips) - l0), "clocks": clocks}), flush=True)
+
+
+def run_c5(args, W, H, desc):
+    """BASELINE config 5: one canvas cut into row bands, one band per GPU (strong scaling).  Per frame: level-0
+    halo rows are exchanged with the neighbouring bands (NCCL point-to-point over NVLink), every band regenerates
+    the mip rows it reads and composites its tiles."""
+    import numpy as np
+    import torch
+    import dplug_b200 as b2
+    from dplug_b200 import synth, sharding as sh
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    stream = torch.cuda.current_stream()
+    bands, plan = sh.halo_plan(W, H, world)
+    y0, y1 = bands[rank]
+    c = b2.PBRCompositor(local, band=(y0, y1) if world > 1 else None)
+    c.resizeBuffers(W, H, 64, 64)
+    c.set_stream(stream.cuda_stream)
+    c.setSkybox(synth.skybox())
+    # synthetic content: one 512-row block of the generator repeated down the band (generating 268 Mpix with
+    # numpy would take minutes); every rank uploads ONLY its own rows, halos arrive through the exchange
+    blk = 512
+    d, m, z = (synth.diffuse(W, blk, synth.SEED + rank), synth.material(W, blk, synth.SEED + rank), synth.depth(W, blk, synth.SEED + rank))
+    for yy in range(y0, y1, blk):
+        n = min(blk, y1 - yy)
+        c.diffuseMap.uploadRows(0, d[:n], yy); c.materialMap.uploadRows(0, m[:n], yy); c.depthMap.uploadRows(0, z[:n], yy)
+    stores = {}
+    for which in (sh.DIFFUSE, sh.DEPTH):
+        w_, h_, pitch, ptr, first = c.map(which).levelInfo(0)
+        slo, shi, _, _ = c.bandRows(which, 0)
+        t = torch.as_tensor(_DevView(ptr, pitch * (shi - slo)), device="cuda:%d" % local).view(shi - slo, pitch)
+        stores[which] = (t, first)
+    tiles = b2.BoxArray(b2.tileAreas([(0, y0, W, y1)], 64, 64))
+    whole = b2.BoxArray([(0, 0, W, H)])
+
+    def step():
+        if world > 1:
+            sh.exchange_halos(rank, world, plan, stores, dist)
+        c.regenerateMipmaps(whole)
+        c.compositeTile(None, tiles)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    l0 = c.kernelLaunches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start(); time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    if rank == 0:
+        B = algorithmic_bytes_frame(W, H)
+        peak, src = _peak()
+        halo = sum((hi - lo) * W * (4 if which == sh.DIFFUSE else 2) for r in plan for (which, _, lo, hi) in plan[r])
+        print(json.dumps({
+            "metric": "composited Mpix/s (full PBR frame)", "value": W * H * args.steps / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (512-row generator block repeated)",
+            "config": {"workload": desc, "tile": "64x64", "parallelism": "%d row bands, level-0 halo exchange (%d bytes per frame in total)" % (world, halo),
+                       "l2": "inputs larger than L2 (%.0f MB per band)" % (B / world / 1e6)},
+            "frame_roofline_frac": (B * args.steps / (ms * 1e-3) / 1e9) / (peak * world), "peak_source": src,
+            "gpu_launches": int(c.kernelLaunches() - l0), "clocks": clocks}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -301,7 +446,13 @@ def main():
     args = ap.parse_args()
     W, H, desc = WORKLOADS[args.workload]
     if args.impl == "reference":
+        if args.workload in ("c3", "c5"):
+            W, H, desc = WORKLOADS["c2"]
         run_reference(args, W, H, desc)
+    elif args.workload == "c3":
+        run_c3(args, W, H, desc)
+    elif args.workload == "c5":
+        run_c5(args, W, H, desc)
     else:
         run_b200(args, W, H, desc)
 
