@@ -5,6 +5,7 @@
 // kernel launches.  There is no CPU implementation of any pixel work in this library: if CUDA is not
 // usable every entry point that would touch pixels fails with B2_ERR_NO_DEVICE / B2_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -352,6 +353,8 @@ struct b2pbr {
     Box* dBoxes = nullptr; int boxCap = 0;
     Box* hBoxes = nullptr;           // pinned staging
     cudaEvent_t boxCopied = nullptr;
+    cudaStream_t sIn = nullptr, sOut = nullptr;   // copy streams of the pipelined host path
+    std::vector<cudaEvent_t> pipeEvents;
     std::vector<Box> lastBoxes;
     int lastBoxKind = -1;            // what dBoxes holds: 0 = the caller's areas, 1 = 32-column strips of them
     int nDeviceBoxes = 0;
@@ -633,6 +636,9 @@ void b2pbr_destroy(b2pbr* c) {
     if (c->dBoxes) cudaFree(c->dBoxes);
     if (c->hBoxes) cudaFreeHost(c->hBoxes);
     if (c->boxCopied) cudaEventDestroy(c->boxCopied);
+    if (c->sIn) cudaStreamDestroy(c->sIn);
+    if (c->sOut) cudaStreamDestroy(c->sOut);
+    for (auto e : c->pipeEvents) cudaEventDestroy(e);
     for (auto& t : c->trace) { cudaEventDestroy(t.beg); cudaEventDestroy(t.end); }
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -838,6 +844,96 @@ int b2pbr_download_swizzled(b2pbr* c, int pf, void* host, size_t host_pitch, con
     return B2_OK;
 }
 
+// Full-frame host call as a 3-stage pipeline over row chunks: while chunk k+1 of the three level-0 maps crosses
+// PCIe, the mip rows that became computable are generated and the tiles whose whole sampling footprint (bloom:
+// 94 rows) has arrived are composited, and finished tile rows travel back on a third stream.
+// Same results as the sequential path: the work is only re-ordered (every mip row is generated once, from
+// complete sources; every area is composited once).
+static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, int n_areas,
+                            b2_imageref dI, b2_imageref mI, b2_imageref zI) {
+    const int W = c->W, H = c->H;
+    CU(cudaSetDevice(c->device));
+    if (!c->sIn) {
+        CU(cudaStreamCreateWithFlags(&c->sIn, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c->sOut, cudaStreamNonBlocking));
+    }
+    int chunk = ((H + 7) / 8 + 63) / 64 * 64;
+    if (chunk < 128) chunk = 128;
+    const int nChunks = (H + chunk - 1) / chunk;
+    while ((int)c->pipeEvents.size() < 2 * nChunks + 1) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->pipeEvents.push_back(e);
+    }
+    // uploads must not overtake kernels of a previous call that still read the maps
+    CU(cudaEventRecord(c->pipeEvents[2 * nChunks], c->stream));
+    CU(cudaStreamWaitEvent(c->sIn, c->pipeEvents[2 * nChunks], 0));
+    std::vector<int> order(n_areas);
+    for (int k = 0; k < n_areas; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return areas[a].max_y < areas[b].max_y; });
+    size_t pos = 0;
+    int cPrev = 0;
+    int genD[kMaxDiffuseLevels] = {0}, genZ[kMaxDepthLevels] = {0};
+    const int nD = (int)c->diffuse->levels.size(), nZ = (int)c->depth->levels.size();
+    std::vector<b2_box2i> subset, merged;
+    for (int k = 0; k < nChunks; ++k) {
+        const int y0 = k * chunk, y1 = y0 + chunk < H ? y0 + chunk : H;
+        struct { b2mip* m; b2_imageref im; } ups[3] = {{c->diffuse, dI}, {c->material, mI}, {c->depth, zI}};
+        for (auto& u : ups) {
+            const DevLevel& L = u.m->levels[0];
+            CU(cudaMemcpy2DAsync(L.base + (size_t)(y0 - L.y0) * L.pitch, (size_t)L.pitch, (const uint8_t*)u.im.pixels + (size_t)y0 * u.im.pitch,
+                                 u.im.pitch, (size_t)W * u.m->elem, (size_t)(y1 - y0), cudaMemcpyHostToDevice, c->sIn));
+        }
+        CU(cudaEventRecord(c->pipeEvents[2 * k], c->sIn));
+        CU(cudaStreamWaitEvent(c->stream, c->pipeEvents[2 * k], 0));
+        // rows that can be composited now: every level-0 row their passes (and the mip rows they sample) read is < y1
+        int cNew = cPrev;
+        int nd[kMaxDiffuseLevels][2], nz[kMaxDepthLevels][2];
+        if (y1 == H) cNew = H;
+        else
+            for (int t = cPrev + 64; t <= H; t += 64) {
+                computeBandNeeds(W, H, cPrev, t, nd, nz);
+                if (nd[0][1] > y1 || nz[0][1] > y1) break;
+                cNew = t;
+            }
+        if (cNew == cPrev) continue;
+        computeBandNeeds(W, H, cPrev, cNew, nd, nz);
+        for (int l = 1; l < nD; ++l) {
+            if (nd[l][1] <= genD[l]) continue;
+            int q = l == 1 ? B2_QUALITY_BOX_ALPHACOV_PREMUL : B2_QUALITY_CUBIC;   // graphics.d:1380-1384
+            int rc = mipGenerateLevel(c->diffuse, l, q, b2_box2i{0, genD[l], c->diffuse->levels[l].w, nd[l][1]});
+            if (rc) return rc;
+            genD[l] = nd[l][1];
+            c->launches++;
+        }
+        for (int l = 1; l < nZ; ++l) {
+            if (nz[l][1] <= genZ[l]) continue;
+            int q = l >= 3 ? B2_QUALITY_CUBIC : B2_QUALITY_BOX;                    // graphics.d:1414
+            int rc = mipGenerateLevel(c->depth, l, q, b2_box2i{0, genZ[l], c->depth->levels[l].w, nz[l][1]});
+            if (rc) return rc;
+            genZ[l] = nz[l][1];
+            c->launches++;
+        }
+        subset.clear();
+        while (pos < order.size() && areas[order[pos]].max_y <= cNew) subset.push_back(areas[order[pos++]]);
+        if (!subset.empty()) {
+            int rc = pbrComposite(c, subset.data(), (int)subset.size(), nullptr, nullptr, nullptr);
+            if (rc) return rc;
+            CU(cudaEventRecord(c->pipeEvents[2 * k + 1], c->stream));
+            CU(cudaStreamWaitEvent(c->sOut, c->pipeEvents[2 * k + 1], 0));
+            mergeRects(subset.data(), (int)subset.size(), merged);
+            for (const b2_box2i& r : merged)
+                CU(cudaMemcpy2DAsync((uint8_t*)wfb.pixels + (size_t)r.min_y * wfb.pitch + (size_t)r.min_x * 4, wfb.pitch,
+                                     c->out.base + (size_t)(r.min_y - c->out.y0) * c->out.pitch + (size_t)r.min_x * 4, (size_t)c->out.pitch,
+                                     (size_t)boxW(r) * 4, (size_t)boxH(r), cudaMemcpyDeviceToHost, c->sOut));
+        }
+        cPrev = cNew;
+    }
+    CU(cudaStreamSynchronize(c->sOut));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
 int b2pbr_composite_tile_host(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, int n_areas, const b2_box2i* update_rects,
                               int n_update, b2_imageref diffuse_l0, b2_imageref material_l0, b2_imageref depth_l0) {
     if (!c || !c->diffuse) return fail(B2_ERR_STATE, "compositeTile(host) before resizeBuffers");
@@ -846,6 +942,10 @@ int b2pbr_composite_tile_host(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, 
         return fail(B2_ERR_INVALID, "compositeTile(host): image size differs from resizeBuffers size");
     if (!update_rects) { update_rects = areas; n_update = n_areas; }
     int rc;
+    // whole frame dirty (first frame, resize, animated UI): overlap PCIe with the kernels
+    if (!c->banded && !c->profile && n_update == 1 && update_rects[0].min_x == 0 && update_rects[0].min_y == 0 &&
+        update_rects[0].max_x == c->W && update_rects[0].max_y == c->H && c->H >= 512)
+        return pbrHostPipelined(c, wfb, areas, n_areas, diffuse_l0, material_l0, depth_l0);
     traceBegin(c, "upload dirty rects");
     if ((rc = b2mip_upload(c->diffuse, 0, diffuse_l0.pixels, diffuse_l0.pitch, update_rects, n_update))) return rc;
     if ((rc = b2mip_upload(c->material, 0, material_l0.pixels, material_l0.pitch, update_rects, n_update))) return rc;
