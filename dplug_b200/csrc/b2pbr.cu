@@ -516,7 +516,10 @@ static int pbrUploadBoxes(b2pbr* c, const b2_box2i* areas, int n, int kind) {
     return B2_OK;
 }
 
-static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, b2mip* material, b2mip* depth) {
+// `workFirst`/`workCount` (optional) restrict the launch to a sub-range of the device work list built from `areas`
+// (used by the pipelined host path, which uploads the list of the whole frame once and launches it in slices).
+static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, b2mip* material, b2mip* depth,
+                        int workFirst = 0, int workCount = -1, bool* usedFast = nullptr) {
     if (!c->outAlloc) return fail(B2_ERR_STATE, "compositeTile before resizeBuffers (compositor.d:41)");
     if (!diffuse) diffuse = c->diffuse;
     if (!material) material = c->material;
@@ -539,7 +542,10 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
     const bool fast = c->mode == B2_MODE_FAST && (int)diffuse->levels.size() >= kMaxDiffuseLevels && (int)depth->levels.size() >= kMaxDepthLevels;
     int rc = pbrUploadBoxes(c, areas, n, fast ? 1 : 0);
     if (rc) return rc;
+    if (usedFast) *usedFast = fast;
     if (c->nDeviceBoxes == 0) return B2_OK;
+    if (workCount < 0) workCount = c->nDeviceBoxes - workFirst;
+    if (workCount == 0) return B2_OK;
     PbrArgs A;
     memset(&A, 0, sizeof(A));
     A.nDiffuse = (int)diffuse->levels.size();
@@ -553,7 +559,7 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
     for (int l = 0; l < A.nSky; ++l) A.sky[l] = c->sky->levels[l];
     A.out = c->out;
     A.W = c->W; A.H = c->H;
-    A.boxes = c->dBoxes; A.nBoxes = c->nDeviceBoxes;
+    A.boxes = c->dBoxes + workFirst; A.nBoxes = workCount;
     A.rsqrtTab = c->dRsqrt; A.expTab = c->dExpTab;
     const b2pbr_params& p = c->params;
     memcpy(A.light1, p.light1_color, 12); memcpy(A.light2Dir, p.light2_dir, 12); memcpy(A.light2Col, p.light2_color, 12);
@@ -570,7 +576,7 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
     }
     traceBegin(c, "PBR compositeTile");
     if (fast) launch_pbr_fast(A, c->stream);
-    else launch_pbr_exact(A, c->nDeviceBoxes, c->stream);
+    else launch_pbr_exact(A, A.nBoxes, c->stream);
     c->launches++;
     traceEnd(c);
     CU(cudaGetLastError());
@@ -857,32 +863,57 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
         CU(cudaStreamCreateWithFlags(&c->sIn, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&c->sOut, cudaStreamNonBlocking));
     }
-    int chunk = ((H + 7) / 8 + 63) / 64 * 64;
-    if (chunk < 128) chunk = 128;
-    const int nChunks = (H + chunk - 1) / chunk;
+    // chunk schedule: half of what is left each time (min 64 rows), so the last chunks are small and little work
+    // remains once the final bytes have crossed PCIe, while the copy count (fixed cost each) stays low
+    std::vector<int> bounds{0};
+    while (bounds.back() < H) {
+        int left = H - bounds.back();
+        int ch = ((left + 1) / 2 + 63) / 64 * 64;
+        if (ch < 64) ch = 64;
+        bounds.push_back(bounds.back() + (ch < left ? ch : left));
+    }
+    const int nChunks = (int)bounds.size() - 1;
     while ((int)c->pipeEvents.size() < 2 * nChunks + 1) {
         cudaEvent_t e;
         CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         c->pipeEvents.push_back(e);
     }
+    static const bool dbg = getenv("B2_PIPE_DEBUG") != nullptr;
+    cudaEvent_t d0 = nullptr, d1 = nullptr, d2 = nullptr, d3 = nullptr;
+    if (dbg) { cudaEventCreate(&d0); cudaEventCreate(&d1); cudaEventCreate(&d2); cudaEventCreate(&d3); }
     // uploads must not overtake kernels of a previous call that still read the maps
     CU(cudaEventRecord(c->pipeEvents[2 * nChunks], c->stream));
     CU(cudaStreamWaitEvent(c->sIn, c->pipeEvents[2 * nChunks], 0));
+    if (dbg) cudaEventRecord(d0, c->sIn);
+    // areas in the order their rows complete; the device work list is uploaded once for the whole frame (and kept
+    // across frames while the caller passes the same areas), every stage launches a slice of it
     std::vector<int> order(n_areas);
     for (int k = 0; k < n_areas; ++k) order[k] = k;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return areas[a].max_y < areas[b].max_y; });
+    std::vector<b2_box2i> sorted(n_areas);
+    for (int k = 0; k < n_areas; ++k) sorted[k] = areas[order[k]];
+    const int R = pbr_fast_strip_rows();
+    auto workItems = [&](const b2_box2i& a, bool fast) {
+        if (!fast) return 1;
+        return ((boxH(a) + R - 1) / R) * ((boxW(a) + 31) / 32);
+    };
     size_t pos = 0;
+    int workPos = 0;
     int cPrev = 0;
     int genD[kMaxDiffuseLevels] = {0}, genZ[kMaxDepthLevels] = {0};
     const int nD = (int)c->diffuse->levels.size(), nZ = (int)c->depth->levels.size();
-    std::vector<b2_box2i> subset, merged;
+    std::vector<b2_box2i> merged;
     for (int k = 0; k < nChunks; ++k) {
-        const int y0 = k * chunk, y1 = y0 + chunk < H ? y0 + chunk : H;
+        const int y0 = bounds[k], y1 = bounds[k + 1];
         struct { b2mip* m; b2_imageref im; } ups[3] = {{c->diffuse, dI}, {c->material, mI}, {c->depth, zI}};
         for (auto& u : ups) {
             const DevLevel& L = u.m->levels[0];
-            CU(cudaMemcpy2DAsync(L.base + (size_t)(y0 - L.y0) * L.pitch, (size_t)L.pitch, (const uint8_t*)u.im.pixels + (size_t)y0 * u.im.pitch,
-                                 u.im.pitch, (size_t)W * u.m->elem, (size_t)(y1 - y0), cudaMemcpyHostToDevice, c->sIn));
+            uint8_t* dst = L.base + (size_t)(y0 - L.y0) * L.pitch;
+            const uint8_t* src = (const uint8_t*)u.im.pixels + (size_t)y0 * u.im.pitch;
+            if ((size_t)L.pitch == u.im.pitch && (size_t)W * u.m->elem == u.im.pitch)   // gapless on both sides: one linear copy
+                CU(cudaMemcpyAsync(dst, src, u.im.pitch * (size_t)(y1 - y0), cudaMemcpyHostToDevice, c->sIn));
+            else
+                CU(cudaMemcpy2DAsync(dst, (size_t)L.pitch, src, u.im.pitch, (size_t)W * u.m->elem, (size_t)(y1 - y0), cudaMemcpyHostToDevice, c->sIn));
         }
         CU(cudaEventRecord(c->pipeEvents[2 * k], c->sIn));
         CU(cudaStreamWaitEvent(c->stream, c->pipeEvents[2 * k], 0));
@@ -914,14 +945,21 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
             genZ[l] = nz[l][1];
             c->launches++;
         }
-        subset.clear();
-        while (pos < order.size() && areas[order[pos]].max_y <= cNew) subset.push_back(areas[order[pos++]]);
-        if (!subset.empty()) {
-            int rc = pbrComposite(c, subset.data(), (int)subset.size(), nullptr, nullptr, nullptr);
+        const size_t first = pos;
+        while (pos < sorted.size() && sorted[pos].max_y <= cNew) ++pos;
+        if (pos > first) {
+            bool fast = false;
+            // first call uploads (or re-uses) the list of the whole frame and tells which kernel will run
+            int rc = pbrComposite(c, sorted.data(), n_areas, nullptr, nullptr, nullptr, 0, 0, &fast);
             if (rc) return rc;
+            int cnt = 0;
+            for (size_t q = first; q < pos; ++q) cnt += workItems(sorted[q], fast);
+            rc = pbrComposite(c, sorted.data(), n_areas, nullptr, nullptr, nullptr, workPos, cnt, nullptr);
+            if (rc) return rc;
+            workPos += cnt;
             CU(cudaEventRecord(c->pipeEvents[2 * k + 1], c->stream));
             CU(cudaStreamWaitEvent(c->sOut, c->pipeEvents[2 * k + 1], 0));
-            mergeRects(subset.data(), (int)subset.size(), merged);
+            mergeRects(sorted.data() + first, (int)(pos - first), merged);
             for (const b2_box2i& r : merged)
                 CU(cudaMemcpy2DAsync((uint8_t*)wfb.pixels + (size_t)r.min_y * wfb.pitch + (size_t)r.min_x * 4, wfb.pitch,
                                      c->out.base + (size_t)(r.min_y - c->out.y0) * c->out.pitch + (size_t)r.min_x * 4, (size_t)c->out.pitch,
@@ -929,8 +967,15 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
         }
         cPrev = cNew;
     }
+    if (dbg) { cudaEventRecord(d1, c->sIn); cudaEventRecord(d2, c->stream); cudaEventRecord(d3, c->sOut); }
     CU(cudaStreamSynchronize(c->sOut));
     CU(cudaStreamSynchronize(c->stream));
+    if (dbg) {
+        float a = 0, b = 0, e = 0;
+        cudaEventElapsedTime(&a, d0, d1); cudaEventElapsedTime(&b, d0, d2); cudaEventElapsedTime(&e, d0, d3);
+        fprintf(stderr, "[b2pbr pipe] chunks=%d  H2D done %.3f ms, kernels done %.3f ms, D2H done %.3f ms\n", nChunks, a, b, e);
+        cudaEventDestroy(d0); cudaEventDestroy(d1); cudaEventDestroy(d2); cudaEventDestroy(d3);
+    }
     return B2_OK;
 }
 
