@@ -354,6 +354,8 @@ struct b2pbr {
     Box* hBoxes = nullptr;           // pinned staging
     cudaEvent_t boxCopied = nullptr;
     cudaStream_t sIn = nullptr, sOut = nullptr;   // copy streams of the pipelined host path
+    cudaStream_t sAux = nullptr;                  // the depth pyramid is regenerated next to the diffuse one
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     std::vector<cudaEvent_t> pipeEvents;
     std::vector<Box> lastBoxes;
     int lastBoxKind = -1;            // what dBoxes holds: 0 = the caller's areas, 1 = 32-column strips of them
@@ -642,6 +644,9 @@ void b2pbr_destroy(b2pbr* c) {
     if (c->dBoxes) cudaFree(c->dBoxes);
     if (c->hBoxes) cudaFreeHost(c->hBoxes);
     if (c->boxCopied) cudaEventDestroy(c->boxCopied);
+    if (c->sAux) cudaStreamDestroy(c->sAux);
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->evJoin) cudaEventDestroy(c->evJoin);
     if (c->sIn) cudaStreamDestroy(c->sIn);
     if (c->sOut) cudaStreamDestroy(c->sOut);
     for (auto e : c->pipeEvents) cudaEventDestroy(e);
@@ -755,8 +760,24 @@ int b2pbr_regenerate_mipmaps(b2pbr* c, const b2_box2i* rects, int n) {
     if (n <= 0) return B2_OK;  // graphics.d:1358-1360
     std::vector<b2_box2i> s0(rects, rects + n), s1(rects, rects + n);
     uint64_t before = c->diffuse->launches + c->depth->launches;
+    CU(cudaSetDevice(c->device));
+    // The two pyramids are independent (the reference builds them one after the other on one thread,
+    // graphics.d:1369-1370): the depth chain runs on a second stream beside the diffuse chain and joins before
+    // anything else is enqueued on the compositor's stream.
+    const bool fork = !c->profile;
+    if (fork) {
+        if (!c->sAux) {
+            CU(cudaStreamCreateWithFlags(&c->sAux, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
+        }
+        CU(cudaEventRecord(c->evFork, c->stream));
+        CU(cudaStreamWaitEvent(c->sAux, c->evFork, 0));
+        c->depth->stream = c->sAux;
+    }
+    int err = B2_OK;
     traceBegin(c, "diffuse mipmap");
-    for (int level = 1; level < (int)c->diffuse->levels.size(); ++level) {
+    for (int level = 1; level < (int)c->diffuse->levels.size() && !err; ++level) {
         int q = level == 1 ? B2_QUALITY_BOX_ALPHACOV_PREMUL : B2_QUALITY_CUBIC;  // graphics.d:1380-1384
         for (auto& area : s0) {
             const DevLevel& Pv = c->diffuse->levels[level - 1];
@@ -766,14 +787,13 @@ int b2pbr_regenerate_mipmaps(b2pbr* c, const b2_box2i* rects, int n) {
                 if (r.min_y < c->needD[level][0]) r.min_y = c->needD[level][0];
                 if (r.max_y > c->needD[level][1]) r.max_y = c->needD[level][1];
             }
-            int rc = mipGenerateLevel(c->diffuse, level, q, r);
-            if (rc) return rc;
+            if ((err = mipGenerateLevel(c->diffuse, level, q, r))) break;
         }
     }
     traceEnd(c);
     // depth: replicateBordersTouching(area) (graphics.d:1406-1408) is clamp-to-edge addressing on the device
     traceBegin(c, "depth mipmap");
-    for (int level = 1; level < (int)c->depth->levels.size(); ++level) {
+    for (int level = 1; level < (int)c->depth->levels.size() && !err; ++level) {
         int q = level >= 3 ? B2_QUALITY_CUBIC : B2_QUALITY_BOX;  // graphics.d:1414
         for (auto& area : s1) {
             const DevLevel& Pv = c->depth->levels[level - 1];
@@ -783,11 +803,16 @@ int b2pbr_regenerate_mipmaps(b2pbr* c, const b2_box2i* rects, int n) {
                 if (r.min_y < c->needZ[level][0]) r.min_y = c->needZ[level][0];
                 if (r.max_y > c->needZ[level][1]) r.max_y = c->needZ[level][1];
             }
-            int rc = mipGenerateLevel(c->depth, level, q, r);
-            if (rc) return rc;
+            if ((err = mipGenerateLevel(c->depth, level, q, r))) break;
         }
     }
     traceEnd(c);
+    if (fork) {
+        c->depth->stream = c->stream;
+        CU(cudaEventRecord(c->evJoin, c->sAux));
+        CU(cudaStreamWaitEvent(c->stream, c->evJoin, 0));
+    }
+    if (err) return err;
     c->launches += c->diffuse->launches + c->depth->launches - before;
     return B2_OK;
 }

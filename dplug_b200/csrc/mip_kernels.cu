@@ -23,7 +23,12 @@ __device__ __forceinline__ uint32_t box4(uint32_t a, uint32_t b, uint32_t c, uin
 // generateLevelBoxAlphaCovIntoPremulRGBA — mipmap.d:861-896 (non-legacy branch)
 __device__ __forceinline__ void premulAccum(uint32_t p, float& r, float& g, float& b, float& a, bool first) {
     const float inv = 1.0f / 255;
-    float fr = (float)(p & 0xff), fg = (float)((p >> 8) & 0xff), fb = (float)((p >> 16) & 0xff), fa = (float)(p >> 24);
+    // byte -> float without I2F (quarter-rate XU pipe, which would bound this kernel): (0x4B000000 | b) is the
+    // float 2^23 + b, the subtraction is exact
+    float fr = __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7440)) - 8388608.0f;
+    float fg = __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7441)) - 8388608.0f;
+    float fb = __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7442)) - 8388608.0f;
+    float fa = __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7443)) - 8388608.0f;
     float al = fa * inv;
     float lr = fr * inv * fr * inv * al;
     float lg = fg * inv * fg * inv * al;
