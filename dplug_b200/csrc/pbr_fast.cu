@@ -49,7 +49,7 @@ struct RowSetup {            // vertical sampler set-up of one row; texel rows a
     float fy[4];
     int ib4, ib5;            // bicubic interval (floor(y_s) + 1) of diffuse levels 4 and 5
     float wy4[4], wy5[4];    // Catmull-Rom weights of the four rows
-    int pad[2];
+    float ey, ey2;           // toEye.y = j / H - 0.5 and its square (legacypbr.d:756, 914), exact
 };
 static_assert(sizeof(RowSetup) % 16 == 0, "RowSetup is read with 128-bit shared loads");
 
@@ -101,6 +101,15 @@ __device__ __forceinline__ uint32_t cvtSatU8(float f) {  // truncate, clamp to [
     uint32_t r;
     asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(f));
     return r & 0xffu;
+}
+
+// RSQRTSS emulation for operands that are provably positive normal floats (all three uses here): the table entry of
+// the bin with the exponent moved by floor((e - 126) / 2) = (bits >> 24) - 63, i.e. entry + (63 << 23) - ((bits >> 1)
+// & 0x7f800000).  Same value as rsqrtss_x86() on that domain; a zero operand yields +inf like the instruction.
+__device__ __forceinline__ float rsqrtssPos(const uint32_t* __restrict__ tab, float x) {
+    const uint32_t b = __float_as_uint(x);
+    const uint32_t r = __ldg(tab + ((b >> 13) & 0x7ffu)) + 0x1F800000u - ((b >> 1) & 0x7F800000u);
+    return b == 0u ? __uint_as_float(0x7f800000u) : __uint_as_float(r);
 }
 
 // ---- sampler coordinates.  (p + 0.5) * 2^-l - 0.5 == n / 2^(l+1) with n = 2p + 1 - 2^l: integer shifts give
@@ -217,7 +226,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         float t;
         cubCoord(4, j, rs.ib4, t); catmullRomWeights(t, rs.wy4);
         cubCoord(5, j, rs.ib5, t); catmullRomWeights(t, rs.wy5);
-        rs.pad[0] = rs.pad[1] = 0;
+        rs.ey = __fsub_rn(__fmul_rn((float)j, P.invH), 0.5f);
+        rs.ey2 = __fmul_rn(rs.ey, rs.ey);
         S.rows[lane] = rs;
     }
     __syncwarp();
@@ -307,6 +317,22 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         }
         const RowSetup& rs = S.rows[j - box.miny];   // broadcast shared loads
 
+        // rolling rows of levels 1..3: the diffuse and depth pyramids share the texel rows, one warp-uniform test
+        // per level refreshes both (the rows are recomputed from the staged windows, so the result does not depend
+        // on where the strip starts)
+        if (rs.iy[0] != rowA1 || rs.iy1[0] != rowB1) {
+            if (needMipsD) { F3 na = hrow1(rs.iy[0]), nb = hrow1(rs.iy1[0]); a1 = na; d1 = nb - na; }
+            if (needMipsZ) { float na = zrow1(rs.iy[0]), nb = zrow1(rs.iy1[0]); za1 = na; zd1 = nb - na; }
+        }
+        if (rs.iy[1] != rowA2 || rs.iy1[1] != rowB2) {
+            if (needMipsD) { F3 na = hrow2(rs.iy[1]), nb = hrow2(rs.iy1[1]); a2 = na; d2 = nb - na; }
+            if (needMipsZ) { float na = zrow2(rs.iy[1]), nb = zrow2(rs.iy1[1]); za2 = na; zd2 = nb - na; }
+        }
+        if (rs.iy[2] != rowA3 || rs.iy1[2] != rowB3) {
+            if (needMipsD) { F3 na = hrow3(rs.iy[2]), nb = hrow3(rs.iy1[2]); a3 = na; d3 = nb - na; }
+            if (needMipsZ) { float na = zrow3(rs.iy[2]), nb = zrow3(rs.iy1[2]); za3 = na; zd3 = nb - na; }
+        }
+
         const F3 base = rgbOf(diffusePx) * div255;
         const float rough = byteToFloat(materialPx, 0) * div255;
         const float metal = byteToFloat(materialPx, 1) * div255;
@@ -340,7 +366,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
             float yz = __fadd_rn(__fadd_rn(__fadd_rn(yz0, yz1), yz2), yz3);
             float vx = -xz, vy = yz;
             float len2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), nz2);  // (+ w*w = +0 dropped)
-            float inv = rsqrtss_x86(P.rsqrtTab, len2);
+            float inv = rsqrtssPos(P.rsqrtTab, len2);
             nx = vx * inv; ny = vy * inv; nzc = 0.382658847856f * inv;
             // variance (legacypbr.d:356-377): second differences of the 3x3 window.  The reference sums raw depths
             // (exact); here they are rebuilt from d (relative error ~1e-7, the variance feeds no RSQRTSS)
@@ -356,18 +382,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
 
         // ---- PassAmbientOcclusion (legacypbr.d:400-444): depth levels 1..4, bilinear
         if (needMipsZ) {
-            if (rs.iy[0] != rowA1 || rs.iy1[0] != rowB1) {
-                float na = zrow1(rs.iy[0]), nb = zrow1(rs.iy1[0]);
-                za1 = na; zd1 = nb - na;
-            }
-            if (rs.iy[1] != rowA2 || rs.iy1[1] != rowB2) {
-                float na = zrow2(rs.iy[1]), nb = zrow2(rs.iy1[1]);
-                za2 = na; zd2 = nb - na;
-            }
-            if (rs.iy[2] != rowA3 || rs.iy1[2] != rowB3) {
-                float na = zrow3(rs.iy[2]), nb = zrow3(rs.iy1[2]);
-                za3 = na; zd3 = nb - na;
-            }
             if (rs.iy[3] != rowA4 || rs.iy1[3] != rowB4) {
                 float na = zrow4(rs.iy[3]), nb = zrow4(rs.iy1[3]);
                 za4 = na; zd4 = nb - na;
@@ -413,9 +427,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         // toEye (legacypbr.d:756-757, 914-915): exact operand for RSQRTSS, shared by specular and skybox
         float ex = eyeX, ey = 0, ez = 1.0f;
         if (mask & 0x30u) {
-            ey = __fsub_rn(__fmul_rn((float)j, P.invH), 0.5f);
-            float len2 = __fadd_rn(__fadd_rn(eyeX2, __fmul_rn(ey, ey)), 1.0f);
-            float inv = rsqrtss_x86(P.rsqrtTab, len2);
+            ey = rs.ey;
+            float len2 = __fadd_rn(__fadd_rn(eyeX2, rs.ey2), 1.0f);
+            float inv = rsqrtssPos(P.rsqrtTab, len2);
             ex = __fmul_rn(eyeX, inv); ey = __fmul_rn(ey, inv); ez = inv;  // 1.0f * inv
         }
 
@@ -423,7 +437,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         if (mask & 0x10u) {
             float hx = __fsub_rn(ex, -P.light3Dir[0]), hy = __fsub_rn(ey, -P.light3Dir[1]), hz = __fsub_rn(ez, -P.light3Dir[2]);
             float hl2 = __fadd_rn(__fadd_rn(__fmul_rn(hx, hx), __fmul_rn(hy, hy)), __fmul_rn(hz, hz));
-            float inv = rsqrtss_x86(P.rsqrtTab, hl2);
+            float inv = rsqrtssPos(P.rsqrtTab, hl2);
             float sf = fmaf(hz * inv, nzc, fmaf(hy * inv, ny, (hx * inv) * nx));
             sf = fmaxf(sf, 1e-3f);
             float exponent = __ldg(P.expTab + roughByte);
@@ -488,18 +502,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         // ---- PassEmissiveContribution (legacypbr.d:948-1007, non-legacy branch): diffuse levels 1..3 bilinear,
         // 4 and 5 bicubic
         if (needMipsD) {
-            if (rs.iy[0] != rowA1 || rs.iy1[0] != rowB1) {   // warp-uniform
-                F3 na = hrow1(rs.iy[0]), nb = hrow1(rs.iy1[0]);   // both rows: results independent of the strip cut
-                a1 = na; d1 = nb - na;
-            }
-            if (rs.iy[1] != rowA2 || rs.iy1[1] != rowB2) {
-                F3 na = hrow2(rs.iy[1]), nb = hrow2(rs.iy1[1]);   // both rows: results independent of the strip cut
-                a2 = na; d2 = nb - na;
-            }
-            if (rs.iy[2] != rowA3 || rs.iy1[2] != rowB3) {
-                F3 na = hrow3(rs.iy[2]), nb = hrow3(rs.iy1[2]);   // both rows: results independent of the strip cut
-                a3 = na; d3 = nb - na;
-            }
             if (rs.ib4 != base4) {
                 if (rs.ib4 == base4 + 1) { p4[0] = p4[1]; p4[1] = p4[2]; p4[2] = p4[3]; p4[3] = crow4(rs.ib4, 3); }
                 else {
