@@ -20,7 +20,7 @@ UNITS = [
     ("b2pbr.cu", ["-fmad=false"]),
     ("mip_kernels.cu", ["-fmad=false"]),
     ("pbr_exact.cu", ["-fmad=false"]),
-    ("pbr_fast.cu", ["-DB2_MIN_CTAS=%s" % os.environ.get("B2_MIN_CTAS", "3")]),
+    ("pbr_fast.cu", ["-DB2_MIN_CTAS=%s" % os.environ.get("B2_MIN_CTAS", "4")]),
 ]
 
 
