@@ -81,6 +81,9 @@ SIGNATURES = {
     "b2pbr_download_swizzled": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(box2i), C.c_int]),
     "b2_band_need_rows": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_int)] * 2),
     "b2pbr_band_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4),
+    "b2pbr_graph_begin": (C.c_int, [C.c_void_p]),
+    "b2pbr_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "b2pbr_graph_launch": (C.c_int, [C.c_void_p, C.c_int]),
     "b2pbr_sync": (C.c_int, [C.c_void_p]),
     "b2pbr_composite_raw": (C.c_int, [C.c_void_p, C.POINTER(box2i), C.c_int]),
     "b2pbr_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),

@@ -186,6 +186,18 @@ class PBRCompositor:
         _lib.check(self._l.b2pbr_band_rows(self._h, which, level, *[C.byref(x) for x in v]))
         return tuple(x.value for x in v)
 
+    def graphBegin(self):
+        """start recording this object's device work into a CUDA graph"""
+        _lib.check(self._l.b2pbr_graph_begin(self._h))
+
+    def graphEnd(self):
+        gid = C.c_int()
+        _lib.check(self._l.b2pbr_graph_end(self._h, C.byref(gid)))
+        return gid.value
+
+    def graphLaunch(self, gid):
+        _lib.check(self._l.b2pbr_graph_launch(self._h, gid))
+
     def sync(self):
         _lib.check(self._l.b2pbr_sync(self._h))
 

@@ -354,6 +354,10 @@ struct b2pbr {
     Box* hBoxes = nullptr;           // pinned staging
     cudaEvent_t boxCopied = nullptr;
     cudaStream_t sIn = nullptr, sOut = nullptr;   // copy streams of the pipelined host path
+    std::vector<cudaGraphExec_t> graphs;          // frames recorded with b2pbr_graph_begin / _end
+    std::vector<uint64_t> graphLaunches;          // kernels each recorded graph launches
+    uint64_t launchesAtCapture = 0;
+    bool capturing = false;
     cudaStream_t sAux = nullptr;                  // the depth pyramid is regenerated next to the diffuse one
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     std::vector<cudaEvent_t> pipeEvents;
@@ -487,6 +491,7 @@ static void traceEnd(b2pbr* c) {
 static int pbrUploadBoxes(b2pbr* c, const b2_box2i* areas, int n, int kind) {
     bool same = c->lastBoxKind == kind && (int)c->lastBoxes.size() == n && n > 0 && memcmp(c->lastBoxes.data(), areas, sizeof(Box) * n) == 0;
     if (same) return B2_OK;
+    if (c->capturing) return fail(B2_ERR_STATE, "graph capture: composite this area list once before recording it (its work list is uploaded then)");
     std::vector<Box> work;
     if (kind == 0) work.assign((const Box*)areas, (const Box*)areas + n);
     else {
@@ -614,6 +619,9 @@ static int pbrCreate(b2pbr** out, int device, bool banded, int y0, int y1) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->ownStream = true;
     CU(cudaEventCreateWithFlags(&c->boxCopied, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&c->sAux, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
     CU(cudaMalloc((void**)&c->dRsqrt, sizeof(kRsqrtssTable)));
     CU(cudaMemcpy(c->dRsqrt, kRsqrtssTable, sizeof(kRsqrtssTable), cudaMemcpyHostToDevice));
     float expTab[256];
@@ -644,6 +652,7 @@ void b2pbr_destroy(b2pbr* c) {
     if (c->dBoxes) cudaFree(c->dBoxes);
     if (c->hBoxes) cudaFreeHost(c->hBoxes);
     if (c->boxCopied) cudaEventDestroy(c->boxCopied);
+    for (auto g : c->graphs) if (g) cudaGraphExecDestroy(g);
     if (c->sAux) cudaStreamDestroy(c->sAux);
     if (c->evFork) cudaEventDestroy(c->evFork);
     if (c->evJoin) cudaEventDestroy(c->evJoin);
@@ -766,11 +775,6 @@ int b2pbr_regenerate_mipmaps(b2pbr* c, const b2_box2i* rects, int n) {
     // anything else is enqueued on the compositor's stream.
     const bool fork = !c->profile;
     if (fork) {
-        if (!c->sAux) {
-            CU(cudaStreamCreateWithFlags(&c->sAux, cudaStreamNonBlocking));
-            CU(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
-        }
         CU(cudaEventRecord(c->evFork, c->stream));
         CU(cudaStreamWaitEvent(c->sAux, c->evFork, 0));
         c->depth->stream = c->sAux;
@@ -1058,6 +1062,38 @@ int b2pbr_band_rows(const b2pbr* c, int map, int level, int* stored_lo, int* sto
     }
     if (need_lo) *need_lo = lo;
     if (need_hi) *need_hi = hi;
+    return B2_OK;
+}
+
+// ---- CUDA graphs: record the device work of one frame (regenerateMipmaps + compositeTile on device-resident maps)
+// once and replay it; the launch-bound chain of small mip kernels then costs one graph launch per frame.
+int b2pbr_graph_begin(b2pbr* c) {
+    if (!c || c->capturing) return fail(B2_ERR_STATE, "graph_begin: bad state");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    c->capturing = true;
+    c->launchesAtCapture = c->launches;
+    return B2_OK;
+}
+int b2pbr_graph_end(b2pbr* c, int* graph_id) {
+    if (!c || !c->capturing || !graph_id) return fail(B2_ERR_STATE, "graph_end: not recording");
+    c->capturing = false;
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamEndCapture(c->stream, &g));
+    cudaGraphExec_t e = nullptr;
+    cudaError_t err = cudaGraphInstantiate(&e, g, 0);
+    cudaGraphDestroy(g);
+    if (err != cudaSuccess) return fail(B2_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(err));
+    c->graphs.push_back(e);
+    c->graphLaunches.push_back(c->launches - c->launchesAtCapture);   // recorded, not executed
+    c->launches = c->launchesAtCapture;
+    *graph_id = (int)c->graphs.size() - 1;
+    return B2_OK;
+}
+int b2pbr_graph_launch(b2pbr* c, int graph_id) {
+    if (!c || graph_id < 0 || graph_id >= (int)c->graphs.size() || !c->graphs[graph_id]) return fail(B2_ERR_INVALID, "graph_launch: bad id");
+    CU(cudaGraphLaunch(c->graphs[graph_id], c->stream));
+    c->launches += c->graphLaunches[graph_id];
     return B2_OK;
 }
 

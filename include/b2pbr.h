@@ -185,6 +185,13 @@ int b2pbr_download_swizzled(b2pbr*, int pixel_format, void* host, size_t host_pi
 /* the same "need" rows as pure host arithmetic (no device, no object): used to plan the halo exchange */
 int b2_band_need_rows(int W, int H, int y0, int y1, int map, int level, int* need_lo, int* need_hi);
 int b2pbr_band_rows(const b2pbr*, int map, int level, int* stored_lo, int* stored_hi, int* need_lo, int* need_hi);
+/* CUDA graph of one frame's device work: between _begin and _end, calls on this object (regenerate_mipmaps,
+ * composite_tile on device maps, composite_raw) are recorded instead of executed; _launch replays them on the
+ * object's stream.  Valid while sizes, rectangle lists and parameters stay the same (pixel contents may change).
+ * The area list must have been composited once before it is recorded. */
+int b2pbr_graph_begin(b2pbr*);
+int b2pbr_graph_end(b2pbr*, int* graph_id);
+int b2pbr_graph_launch(b2pbr*, int graph_id);
 int b2pbr_sync(b2pbr*);
 
 /* SimpleRawCompositor (compositor.d:260-298): copy diffuse RGB, alpha = 255, into the composited twin */

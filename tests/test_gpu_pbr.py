@@ -255,3 +255,31 @@ def test_host_call_full_frame_pipelined(b2, oracle):
     for band in [(0, 0, W, 128), (0, 576, W, 704), (0, H - 84, W, H)]:
         ref.compositeGUI([band])
         _compare(wfb[band[1]:band[3]], np.array(ref.output())[band[1]:band[3]], "pipelined %s" % (band,))
+
+
+def test_cuda_graph_replay(b2):
+    """A frame recorded with graphBegin/graphEnd replays to the same bytes, also after the inputs changed."""
+    W, H = 512, 384
+    d, m, z = synth.frame(W, H)
+    c = b2.PBRCompositor(0); c.resizeBuffers(W, H); c.setSkybox(synth.skybox(128, 96))
+    tiles = b2.BoxArray(b2.tileAreas([(0, 0, W, H)], 64, 64)); whole = b2.BoxArray([(0, 0, W, H)])
+    c.diffuseMap.upload(0, d); c.materialMap.upload(0, m); c.depthMap.upload(0, z)
+    c.regenerateMipmaps(whole); c.compositeTile(None, tiles)
+    want = c.download()
+    n0 = c.kernelLaunches()
+    c.graphBegin(); c.regenerateMipmaps(whole); c.compositeTile(None, tiles); gid = c.graphEnd()
+    assert c.kernelLaunches() == n0          # recording launches nothing
+    c.graphLaunch(gid)
+    assert np.array_equal(c.download(), want) and c.kernelLaunches() == n0 + 10
+    d2, m2, z2 = synth.frame(W, H, synth.SEED + 3)
+    c.diffuseMap.upload(0, d2); c.materialMap.upload(0, m2); c.depthMap.upload(0, z2)
+    c.graphLaunch(gid)
+    got = c.download()
+    c.regenerateMipmaps(whole); c.compositeTile(None, tiles)
+    assert np.array_equal(got, c.download()) and not np.array_equal(got, want)
+    with pytest.raises(b2.B2Error):          # an area list that was never composited cannot be recorded
+        c.graphBegin()
+        try:
+            c.compositeTile(None, b2.tileAreas([(0, 0, W, H)], 32, 32))
+        finally:
+            c.graphEnd()
