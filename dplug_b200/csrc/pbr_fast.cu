@@ -151,7 +151,9 @@ __device__ __forceinline__ void stageWindow(T (*dst)[WW], const DevLevel& L, int
     }
 }
 
-template <bool HAS_SKY>
+// ALL_PASSES: every pass active (the reference's default; CompositorPass.setActive is a debugging aid,
+// compositor.d:222-236) — the per-pass tests then fold away at compile time.
+template <bool HAS_SKY, bool ALL_PASSES>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(const __grid_constant__ PbrArgs P) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
 #pragma unroll
     for (int k = 0; k < 4; ++k) p4[k] = p5[k] = a1;
 
-    const uint32_t mask = P.passMask;
+    const uint32_t mask = ALL_PASSES ? 0xffu : P.passMask;
     const bool needMipsD = (mask & 0x40u) != 0, needMipsZ = (mask & 2u) != 0;
 
     // toEye.x and its square are column constants (legacypbr.d:756, 914) — exact sequence
@@ -470,25 +472,21 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
                 const uint32_t* r0 = rowPtr<uint32_t>(L, s.iy);
                 const uint32_t* r1 = rowPtr<uint32_t>(L, s.iy1);
                 uint32_t ta = __ldg(r0 + s.ix), tb = __ldg(r0 + s.ix1), tc = __ldg(r1 + s.ix), td = __ldg(r1 + s.ix1);
-                uint32_t ua = 0, ub = 0, uc = 0, ud = 0;
-                Bilin s2 = s;
-                if (fl != 0.f) {  // second level of the trilinear blend: issue its loads before using the first
-                    const int level2 = max(0, min(il + 1, P.nSky - 1));
-                    const DevLevel& L2 = P.sky[level2];
-                    s2 = bilinSetup(levelScale(level2), skyx, skyy, L2.w, L2.h);
-                    const uint32_t* q0 = rowPtr<uint32_t>(L2, s2.iy);
-                    const uint32_t* q1 = rowPtr<uint32_t>(L2, s2.iy1);
-                    ua = __ldg(q0 + s2.ix); ub = __ldg(q0 + s2.ix1); uc = __ldg(q1 + s2.ix); ud = __ldg(q1 + s2.ix1);
-                }
+                // second level of the trilinear blend.  The reference returns the first level alone when the
+                // fraction is 0 (mipmap.d:154-155); blending with weight 0 gives the same value, so no branch.
+                const int level2 = max(0, min(il + 1, P.nSky - 1));
+                const DevLevel& L2 = P.sky[level2];
+                const Bilin s2 = bilinSetup(levelScale(level2), skyx, skyy, L2.w, L2.h);
+                const uint32_t* q0 = rowPtr<uint32_t>(L2, s2.iy);
+                const uint32_t* q1 = rowPtr<uint32_t>(L2, s2.iy1);
+                const uint32_t ua = __ldg(q0 + s2.ix), ub = __ldg(q0 + s2.ix1), uc = __ldg(q1 + s2.ix), ud = __ldg(q1 + s2.ix1);
                 F3 A = rgbBiased(ta), B = rgbBiased(tb), C = rgbBiased(tc), D = rgbBiased(td);
                 F3 up = fma3(s.fx, B - A, A), down = fma3(s.fx, D - C, C);
                 sky = fma3(s.fy, down - up, up);
-                if (fl != 0.f) {
-                    F3 A2 = rgbBiased(ua), B2 = rgbBiased(ub), C2 = rgbBiased(uc), D2 = rgbBiased(ud);
-                    F3 up2 = fma3(s2.fx, B2 - A2, A2), down2 = fma3(s2.fx, D2 - C2, C2);
-                    F3 sky1 = fma3(s2.fy, down2 - up2, up2);
-                    sky = fma3(fl, sky1 - sky, sky);
-                }
+                F3 A2 = rgbBiased(ua), B2 = rgbBiased(ub), C2 = rgbBiased(uc), D2 = rgbBiased(ud);
+                F3 up2 = fma3(s2.fx, B2 - A2, A2), down2 = fma3(s2.fx, D2 - C2, C2);
+                F3 sky1 = fma3(s2.fy, down2 - up2, up2);
+                sky = fma3(fl, sky1 - sky, sky);
                 sky = F3{sky.x - 32768.0f, sky.y - 32768.0f, sky.z - 32768.0f};
             }
             float k = metal * (P.skyAmount * div255);
@@ -560,12 +558,21 @@ void launch_pbr_fast(const PbrArgs& args, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !g_attrSet[dev]) {  // > 48 KB of dynamic shared memory is an opt-in, per device
-        cudaFuncSetAttribute(k_pbr_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pbr_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pbr_fast<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pbr_fast<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pbr_fast<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pbr_fast<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         g_attrSet[dev] = true;
     }
-    if (args.nSky > 0) k_pbr_fast<true><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(args);
-    else k_pbr_fast<false><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(args);
+    const bool all = (args.passMask & 0xffu) == 0xffu;
+    const dim3 block(WARPS_PER_CTA * 32);
+    if (args.nSky > 0) {
+        if (all) k_pbr_fast<true, true><<<grid, block, smem, stream>>>(args);
+        else k_pbr_fast<true, false><<<grid, block, smem, stream>>>(args);
+    } else {
+        if (all) k_pbr_fast<false, true><<<grid, block, smem, stream>>>(args);
+        else k_pbr_fast<false, false><<<grid, block, smem, stream>>>(args);
+    }
 }
 
 }  // namespace b2
