@@ -20,32 +20,57 @@ __device__ __forceinline__ uint32_t box4(uint32_t a, uint32_t b, uint32_t c, uin
     return ((lo >> 2) & 0x00ff00ffu) | (((hi >> 2) & 0x00ff00ffu) << 8);
 }
 
-// generateLevelBoxAlphaCovIntoPremulRGBA — mipmap.d:861-896 (non-legacy branch)
-__device__ __forceinline__ void premulAccum(uint32_t p, float& r, float& g, float& b, float& a, bool first) {
-    const float inv = 1.0f / 255;
-    // byte -> float without I2F (quarter-rate XU pipe, which would bound this kernel): (0x4B000000 | b) is the
-    // float 2^23 + b, the subtraction is exact
-    float fr = __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7440)) - 8388608.0f;
-    float fg = __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7441)) - 8388608.0f;
-    float fb = __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7442)) - 8388608.0f;
-    float fa = __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7443)) - 8388608.0f;
-    float al = fa * inv;
-    float lr = fr * inv * fr * inv * al;
-    float lg = fg * inv * fg * inv * al;
-    float lb = fb * inv * fb * inv * al;
-    if (first) { r = lr; g = lg; b = lb; a = al; }
-    else { r = r + lr; g = g + lg; b = b + lb; a = a + al; }
+// generateLevelBoxAlphaCovIntoPremulRGBA — mipmap.d:861-896 (non-legacy branch).
+//
+// The reference's arithmetic is a chain of single IEEE multiplies and adds per channel (no FMA).  Blackwell's packed
+// FP32 pipe (FFMA2: two independent fp32 lanes per instruction) evaluates two channels at once: a product is
+// fma(a, b, -0) and a sum is fma(a, 1, b) — each still ONE correctly rounded operation per lane, so the bytes are
+// the reference's.  Channels are paired (r, g) and (b, a).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {   // exact rounded products
+    f32x2 r;
+    const f32x2 nz = 0x8000000080000000ull;                 // (-0, -0)
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {   // exact rounded sums
+    f32x2 r;
+    const f32x2 one = 0x3f8000003f800000ull;                // (1, 1)
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(one), "l"(b));
+    return r;
+}
+struct Premul2 { f32x2 rg, ba; };
+__device__ __forceinline__ Premul2 premulLinear(uint32_t p) {   // convert_gammaspace_to_linear_premul, mipmap.d:869-878
+    const float invf = 1.0f / 255;
+    const f32x2 inv = pack2(invf, invf);
+    const f32x2 magic = pack2(-8388608.0f, -8388608.0f);
+    // byte -> float without I2F: (0x4B000000 | b) is the float 2^23 + b; the subtraction is exact
+    f32x2 rg = add2(pack2(__uint_as_float(__byte_perm(p, 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7441))), magic);
+    f32x2 ba = add2(pack2(__uint_as_float(__byte_perm(p, 0x4B000000u, 0x7442)), __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7443))), magic);
+    float fb, fa;
+    unpack2(ba, fb, fa);
+    const float al = fa * invf;                                  // res.a = col.a * inv_255
+    const f32x2 al2 = pack2(al, al);
+    f32x2 t = mul2(mul2(mul2(rg, inv), rg), inv);                // ((c * inv) * c) * inv
+    Premul2 o;
+    o.rg = mul2(t, al2);                                         // ... * res.a
+    float lb = fb * invf * fb * invf * al;
+    o.ba = pack2(lb, al);
+    return o;
 }
 __device__ __forceinline__ uint32_t premul4(uint32_t A, uint32_t B, uint32_t C, uint32_t D) {
-    float r, g, b, a;
-    premulAccum(A, r, g, b, a, true);
-    premulAccum(B, r, g, b, a, false);
-    premulAccum(C, r, g, b, a, false);
-    premulAccum(D, r, g, b, a, false);
-    uint32_t ur = (uint32_t)__float2int_rz(r * 0.25f * 255.0f + 0.5f) & 0xff;
-    uint32_t ug = (uint32_t)__float2int_rz(g * 0.25f * 255.0f + 0.5f) & 0xff;
-    uint32_t ub = (uint32_t)__float2int_rz(b * 0.25f * 255.0f + 0.5f) & 0xff;
-    uint32_t ua = (uint32_t)__float2int_rz(a * 0.25f * 255.0f + 0.5f) & 0xff;
+    Premul2 a = premulLinear(A), b = premulLinear(B), c = premulLinear(C), d = premulLinear(D);
+    f32x2 rg = add2(add2(add2(a.rg, b.rg), c.rg), d.rg);         // ((A + B) + C) + D, mipmap.d:886-889
+    f32x2 ba = add2(add2(add2(a.ba, b.ba), c.ba), d.ba);
+    const f32x2 q = pack2(0.25f, 0.25f), s255 = pack2(255.0f, 255.0f), h = pack2(0.5f, 0.5f);
+    rg = add2(mul2(mul2(rg, q), s255), h);                       // mean * 0.25f * 255.0f + 0.5f, mipmap.d:891-894
+    ba = add2(mul2(mul2(ba, q), s255), h);
+    float r_, g_, b_, a_;
+    unpack2(rg, r_, g_); unpack2(ba, b_, a_);
+    uint32_t ur = (uint32_t)__float2int_rz(r_) & 0xff, ug = (uint32_t)__float2int_rz(g_) & 0xff;
+    uint32_t ub = (uint32_t)__float2int_rz(b_) & 0xff, ua = (uint32_t)__float2int_rz(a_) & 0xff;
     return ur | (ug << 8) | (ub << 16) | (ua << 24);
 }
 

@@ -472,21 +472,25 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
                 const uint32_t* r0 = rowPtr<uint32_t>(L, s.iy);
                 const uint32_t* r1 = rowPtr<uint32_t>(L, s.iy1);
                 uint32_t ta = __ldg(r0 + s.ix), tb = __ldg(r0 + s.ix1), tc = __ldg(r1 + s.ix), td = __ldg(r1 + s.ix1);
-                // second level of the trilinear blend.  The reference returns the first level alone when the
-                // fraction is 0 (mipmap.d:154-155); blending with weight 0 gives the same value, so no branch.
-                const int level2 = max(0, min(il + 1, P.nSky - 1));
-                const DevLevel& L2 = P.sky[level2];
-                const Bilin s2 = bilinSetup(levelScale(level2), skyx, skyy, L2.w, L2.h);
-                const uint32_t* q0 = rowPtr<uint32_t>(L2, s2.iy);
-                const uint32_t* q1 = rowPtr<uint32_t>(L2, s2.iy1);
-                const uint32_t ua = __ldg(q0 + s2.ix), ub = __ldg(q0 + s2.ix1), uc = __ldg(q1 + s2.ix), ud = __ldg(q1 + s2.ix1);
+                uint32_t ua = 0, ub = 0, uc = 0, ud = 0;
+                Bilin s2 = s;
+                if (fl != 0.f) {  // second level of the trilinear blend: issue its loads before using the first
+                    const int level2 = max(0, min(il + 1, P.nSky - 1));
+                    const DevLevel& L2 = P.sky[level2];
+                    s2 = bilinSetup(levelScale(level2), skyx, skyy, L2.w, L2.h);
+                    const uint32_t* q0 = rowPtr<uint32_t>(L2, s2.iy);
+                    const uint32_t* q1 = rowPtr<uint32_t>(L2, s2.iy1);
+                    ua = __ldg(q0 + s2.ix); ub = __ldg(q0 + s2.ix1); uc = __ldg(q1 + s2.ix); ud = __ldg(q1 + s2.ix1);
+                }
                 F3 A = rgbBiased(ta), B = rgbBiased(tb), C = rgbBiased(tc), D = rgbBiased(td);
                 F3 up = fma3(s.fx, B - A, A), down = fma3(s.fx, D - C, C);
                 sky = fma3(s.fy, down - up, up);
-                F3 A2 = rgbBiased(ua), B2 = rgbBiased(ub), C2 = rgbBiased(uc), D2 = rgbBiased(ud);
-                F3 up2 = fma3(s2.fx, B2 - A2, A2), down2 = fma3(s2.fx, D2 - C2, C2);
-                F3 sky1 = fma3(s2.fy, down2 - up2, up2);
-                sky = fma3(fl, sky1 - sky, sky);
+                if (fl != 0.f) {
+                    F3 A2 = rgbBiased(ua), B2 = rgbBiased(ub), C2 = rgbBiased(uc), D2 = rgbBiased(ud);
+                    F3 up2 = fma3(s2.fx, B2 - A2, A2), down2 = fma3(s2.fx, D2 - C2, C2);
+                    F3 sky1 = fma3(s2.fy, down2 - up2, up2);
+                    sky = fma3(fl, sky1 - sky, sky);
+                }
                 sky = F3{sky.x - 32768.0f, sky.y - 32768.0f, sky.z - 32768.0f};
             }
             float k = metal * (P.skyAmount * div255);
