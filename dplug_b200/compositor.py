@@ -13,6 +13,16 @@ PF_RGBA8, PF_BGRA8, PF_ARGB8 = 0, 1, 2
 MODE_FAST, MODE_EXACT = 0, 1
 
 
+def liftGammaGainContrastTable(r=(0.0, 1.0, 1.0, 0.0), g=None, b=None):
+    """UIColorCorrection.setLiftGammaGainContrastRGB: (lift, gamma, gain, contrast) per channel -> (3, 256) uint8."""
+    g = r if g is None else g
+    b = r if b is None else b
+    v = (C.c_float * 12)(*[float(x) for x in (tuple(r) + tuple(g) + tuple(b))])
+    out = np.zeros((3, 256), dtype=np.uint8)
+    _lib.lib().b2_lift_gamma_gain_contrast_table(v, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def default_params():
     p = _lib.params()
     _lib.lib().b2pbr_default_params(C.byref(p))
@@ -197,6 +207,21 @@ class PBRCompositor:
 
     def graphLaunch(self, gid):
         _lib.check(self._l.b2pbr_graph_launch(self._h, gid))
+
+    # --- post-composite chain, GUIGraphics.doDraw stages E-H (graphics.d:825-868) ---------------------------
+    def setColorCorrection(self, table):
+        """UIColorCorrection transfer tables: (3, 256) uint8 (red, green, blue) or None."""
+        if table is None:
+            _lib.check(self._l.b2pbr_set_color_correction(self._h, None))
+            return
+        t = np.ascontiguousarray(table, dtype=np.uint8).reshape(768)
+        _lib.check(self._l.b2pbr_set_color_correction(self._h, t.ctypes.data_as(C.c_void_p)))
+
+    def present(self, window, pixelFormat, userOrigin, rects, redrawBorders=False):
+        """blit + colour correction + reorderComponents + resizeContent into `window` ((h, w, 4) uint8)."""
+        _lib.check(self._l.b2pbr_present(self._h, pixelFormat, window.ctypes.data_as(C.c_void_p), window.strides[0], window.shape[1],
+                                         window.shape[0], userOrigin[0], userOrigin[1], _lib.boxes(rects), len(rects), 1 if redrawBorders else 0))
+        return window
 
     def sync(self):
         _lib.check(self._l.b2pbr_sync(self._h))

@@ -24,6 +24,8 @@ void launch_cubic_rgba(const DevLevel& dst, const DevLevel& src, Box r, cudaStre
 void launch_cubic_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
 void launch_copy_diffuse(const DevLevel& dst, const DevLevel& src, const Box* boxes, int n, int grid, cudaStream_t s);
 void launch_swizzle(const DevLevel& dst, const DevLevel& src, Box box, int pf, cudaStream_t s);
+void launch_present(const DevLevel& win, const DevLevel& src, Box box, int dx, int dy, int pf, const uint8_t* lut, cudaStream_t s);
+void launch_fill32(const DevLevel& win, uint32_t value, cudaStream_t s);
 void launch_pbr_exact(const PbrArgs& args, int gridBlocks, cudaStream_t stream);
 void launch_pbr_fast(const PbrArgs& args, cudaStream_t stream);
 int pbr_fast_strip_rows();
@@ -347,6 +349,8 @@ struct b2pbr {
     b2mip *diffuse = nullptr, *material = nullptr, *depth = nullptr, *sky = nullptr;
     DevLevel out{}; uint8_t* outAlloc = nullptr;
     DevLevel swz{}; uint8_t* swzAlloc = nullptr;
+    DevLevel win{}; uint8_t* winAlloc = nullptr;     // device twin of the window buffer (_resizedBuffer, graphics.d:1146)
+    uint8_t* dLut = nullptr; bool lutOn = false;      // UIColorCorrection transfer tables (3 x 256)
     b2pbr_params params;
     uint32_t* dRsqrt = nullptr;
     float* dExpTab = nullptr;
@@ -647,6 +651,8 @@ void b2pbr_destroy(b2pbr* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     pbrFreeMaps(c);
     b2mip_destroy(c->sky);
+    if (c->winAlloc) cudaFree(c->winAlloc);
+    if (c->dLut) cudaFree(c->dLut);
     if (c->dRsqrt) cudaFree(c->dRsqrt);
     if (c->dExpTab) cudaFree(c->dExpTab);
     if (c->dBoxes) cudaFree(c->dBoxes);
@@ -1094,6 +1100,90 @@ int b2pbr_graph_launch(b2pbr* c, int graph_id) {
     if (!c || graph_id < 0 || graph_id >= (int)c->graphs.size() || !c->graphs[graph_id]) return fail(B2_ERR_INVALID, "graph_launch: bad id");
     CU(cudaGraphLaunch(c->graphs[graph_id], c->stream));
     c->launches += c->graphLaunches[graph_id];
+    return B2_OK;
+}
+
+int b2pbr_set_color_correction(b2pbr* c, const uint8_t* table768) {
+    if (!c) return fail(B2_ERR_INVALID, "null compositor");
+    CU(cudaSetDevice(c->device));
+    if (!table768) { c->lutOn = false; return B2_OK; }
+    if (!c->dLut) CU(cudaMalloc((void**)&c->dLut, 768));
+    CU(cudaMemcpyAsync(c->dLut, table768, 768, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->lutOn = true;
+    return B2_OK;
+}
+
+void b2_lift_gamma_gain_contrast_table(const float v[12], uint8_t out[768]) {
+    // UIColorCorrection.setLiftGammaGainContrastRGB (colorcorrection.d:69-116); v = {lift, gamma, gain, contrast} x {r, g, b}
+    for (int ch = 0; ch < 3; ++ch) {
+        const float lift = v[4 * ch], gamma = v[4 * ch + 1], gain = v[4 * ch + 2], contrast = v[4 * ch + 3];
+        for (int b = 0; b < 256; ++b) {
+            float inp = b / 255.0f;
+            float o = gain * (inp + lift * (1 - inp));
+            float a = o < 0 ? 0.f : (o > 1 ? 1.f : o);                 // safePow clamps its base
+            o = (float)std::pow((double)a, (double)(1.0f / gamma));
+            if (o < 0) o = 0;
+            if (o > 1) o = 1;
+            float x = o;                                               // smoothStep(0, 1, o), core/dplug/core/math.d:212-222
+            float ss = x <= 0 ? 0.f : (x >= 1 ? 1.f : x * x * (3 - 2 * x));
+            o = contrast * ss + (1 - contrast) * o;                    // lerp(o, ss, contrast)
+            out[256 * ch + b] = (uint8_t)(0.5f + o * 255.0f);
+        }
+    }
+}
+
+int b2pbr_present(b2pbr* c, int pf, void* window, size_t window_pitch, int window_w, int window_h, int user_x, int user_y,
+                  const b2_box2i* rects, int n, int redraw_borders) {
+    if (!c || !c->outAlloc || !window || pf < 0 || pf > 2 || window_w <= 0 || window_h <= 0 || (n > 0 && !rects))
+        return fail(B2_ERR_INVALID, "present: bad arguments");
+    if (c->banded) return fail(B2_ERR_STATE, "present: not available on a row band");
+    CU(cudaSetDevice(c->device));
+    if (!c->winAlloc || c->win.w != window_w || c->win.h != window_h) {
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->winAlloc) cudaFree(c->winAlloc);
+        c->win.w = window_w; c->win.h = window_h; c->win.y0 = 0; c->win.rows = window_h;
+        c->win.pitch = (int)alignUp((size_t)window_w * 4, 128);
+        CU(cudaMalloc((void**)&c->winAlloc, (size_t)c->win.pitch * window_h));
+        c->win.base = c->winAlloc;
+        redraw_borders = 1;   // a new window buffer has no valid content yet (graphics.d:1091)
+    }
+    const b2_box2i userArea{user_x, user_y, user_x + c->W < window_w ? user_x + c->W : window_w, user_y + c->H < window_h ? user_y + c->H : window_h};
+    if (user_x < 0 || user_y < 0) return fail(B2_ERR_INVALID, "present: negative user-area origin");
+    std::vector<b2_box2i> work;
+    if (redraw_borders) {
+        // resizeContent: fill with black (RGBA/BGRA: 0,0,0,255; ARGB: 255,0,0,0), then copy the whole user area
+        launch_fill32(c->win, pf == B2_PF_ARGB8 ? 0x000000ffu : 0xff000000u, c->stream);
+        c->launches++;
+        work.push_back(b2_box2i{0, 0, userArea.max_x - user_x, userArea.max_y - user_y});
+    } else {
+        for (int k = 0; k < n; ++k) {
+            b2_box2i r = rects[k];   // user coordinates; clip to what is visible in the window
+            if (r.min_x < 0) r.min_x = 0;
+            if (r.min_y < 0) r.min_y = 0;
+            if (r.max_x > userArea.max_x - user_x) r.max_x = userArea.max_x - user_x;
+            if (r.max_y > userArea.max_y - user_y) r.max_y = userArea.max_y - user_y;
+            if (r.max_x > c->W) r.max_x = c->W;
+            if (r.max_y > c->H) r.max_y = c->H;
+            if (boxW(r) > 0 && boxH(r) > 0) work.push_back(r);
+        }
+    }
+    std::vector<b2_box2i> merged;
+    mergeRects(work.data(), (int)work.size(), merged);
+    for (const b2_box2i& r : merged) {
+        launch_present(c->win, c->out, toBox(r), user_x, user_y, pf, c->lutOn ? c->dLut : nullptr, c->stream);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    if (redraw_borders) {
+        CU(cudaMemcpy2DAsync(window, window_pitch, c->win.base, (size_t)c->win.pitch, (size_t)window_w * 4, (size_t)window_h, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        for (const b2_box2i& r : merged)
+            CU(cudaMemcpy2DAsync((uint8_t*)window + (size_t)(r.min_y + user_y) * window_pitch + (size_t)(r.min_x + user_x) * 4, window_pitch,
+                                 c->win.base + (size_t)(r.min_y + user_y) * c->win.pitch + (size_t)(r.min_x + user_x) * 4, (size_t)c->win.pitch,
+                                 (size_t)boxW(r) * 4, (size_t)boxH(r), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
     return B2_OK;
 }
 

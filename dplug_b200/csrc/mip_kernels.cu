@@ -307,6 +307,28 @@ __global__ void __launch_bounds__(256) k_swizzle(DevLevel dst, DevLevel src, Box
     rowPtrW<uint32_t>(dst, j)[i] = o;
 }
 
+// doDraw stages E-H fused (gui/dplug/gui/graphics.d:825-868): the composited pixel goes through the colour-correction
+// transfer tables (applyColorCorrection, pbrwidgets/dplug/pbrwidgets/colorcorrection.d:157-170), is re-ordered to
+// the window's pixel format with alpha = 255 (reorderComponents, graphics.d:1425-1452) and lands in the window
+// buffer at the user-area offset (resizeContent, graphics.d:1465-1511).
+__global__ void __launch_bounds__(256) k_present(DevLevel win, DevLevel src, Box box, int dx, int dy, int pf, const uint8_t* __restrict__ lut) {
+    const int i = box.minx + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = box.miny + blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= box.maxx || j >= box.maxy) return;
+    const uint32_t p = __ldg(rowPtr<uint32_t>(src, j) + i);
+    uint32_t r = p & 0xff, g = (p >> 8) & 0xff, b = (p >> 16) & 0xff;
+    if (lut) { r = __ldg(lut + r); g = __ldg(lut + 256 + g); b = __ldg(lut + 512 + b); }
+    uint32_t o;
+    if (pf == 1) o = b | (g << 8) | (r << 16) | 0xff000000u;        // BGRA8
+    else if (pf == 2) o = 0xffu | (r << 8) | (g << 16) | (b << 24);  // ARGB8
+    else o = r | (g << 8) | (b << 16) | 0xff000000u;                // RGBA8
+    rowPtrW<uint32_t>(win, j + dy)[i + dx] = o;
+}
+__global__ void __launch_bounds__(256) k_fill32(DevLevel win, uint32_t value) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i < win.w && j < win.h) rowPtrW<uint32_t>(win, j)[i] = value;
+}
+
 // ------------------------------------------------------------------------------------------------
 static inline dim3 gridFor(int nx, int ny, dim3 block) { return dim3((nx + block.x - 1) / block.x, (ny + block.y - 1) / block.y); }
 
@@ -338,6 +360,15 @@ void launch_copy_diffuse(const DevLevel& dst, const DevLevel& src, const Box* bo
 void launch_swizzle(const DevLevel& dst, const DevLevel& src, Box box, int pf, cudaStream_t s) {
     dim3 block(32, 8);
     k_swizzle<<<gridFor(box.maxx - box.minx, box.maxy - box.miny, block), block, 0, s>>>(dst, src, box, pf);
+}
+
+void launch_present(const DevLevel& win, const DevLevel& src, Box box, int dx, int dy, int pf, const uint8_t* lut, cudaStream_t s) {
+    dim3 block(32, 8);
+    k_present<<<gridFor(box.maxx - box.minx, box.maxy - box.miny, block), block, 0, s>>>(win, src, box, dx, dy, pf, lut);
+}
+void launch_fill32(const DevLevel& win, uint32_t value, cudaStream_t s) {
+    dim3 block(32, 8);
+    k_fill32<<<gridFor(win.w, win.h, block), block, 0, s>>>(win, value);
 }
 
 }  // namespace b2

@@ -192,6 +192,20 @@ int b2pbr_band_rows(const b2pbr*, int map, int level, int* stored_lo, int* store
 int b2pbr_graph_begin(b2pbr*);
 int b2pbr_graph_end(b2pbr*, int* graph_id);
 int b2pbr_graph_launch(b2pbr*, int graph_id);
+/* SURVEY §8(f) row 1 — the post-composite per-pixel chain of GUIGraphics.doDraw, stages E-H (graphics.d:825-868),
+ * fused into one pass over the composited twin: blit composited -> rendered, UIColorCorrection transfer tables
+ * (pbrwidgets/dplug/pbrwidgets/colorcorrection.d:128-170), reorderComponents(pf) with alpha = 255
+ * (graphics.d:1425-1452) and resizeContent into the window buffer (graphics.d:1465-1511).
+ * `rects` = _rectsToDisplayDisjointed in user coordinates; the user area sits at (user_x, user_y) in the window;
+ * redraw_borders = _redrawBlackBordersAndResizedArea (fill black, copy the whole user area).  Valid when no other
+ * Raw-layer widget draws between the blit and the re-ordering.  Synchronises. */
+int b2pbr_present(b2pbr*, int pixel_format, void* window, size_t window_pitch, int window_w, int window_h,
+                  int user_x, int user_y, const b2_box2i* rects, int n, int redraw_borders);
+/* 3 x 256 transfer tables (red, green, blue) of UIColorCorrection (colorcorrection.d:26-41); NULL = none */
+int b2pbr_set_color_correction(b2pbr*, const uint8_t* rgb_table_768);
+/* setLiftGammaGainContrastRGB (colorcorrection.d:69-116) as a host helper: v = {lift, gamma, gain, contrast} for
+ * r, g, b.  (Table arithmetic uses pow; a caller that needs the reference's exact bytes passes its own table.) */
+void b2_lift_gamma_gain_contrast_table(const float v[12], uint8_t out768[768]);
 int b2pbr_sync(b2pbr*);
 
 /* SimpleRawCompositor (compositor.d:260-298): copy diffuse RGB, alpha = 255, into the composited twin */

@@ -63,6 +63,10 @@ int b2ref_gfx_output(b2ref_gfx*, b2ref_imageref* out);
 int b2ref_gfx_regenerate_mipmaps(b2ref_gfx*, const b2ref_box2i* rects, int n);
 int b2ref_gfx_composite_gui(b2ref_gfx*, const b2ref_box2i* rects, int n);
 
+/* ---- post-composite chain, GUIGraphics.doDraw stages E-H (graphics.d:825-868); `rendered` plays _renderedBuffer */
+int b2ref_present(b2ref_imageref composited, b2ref_imageref rendered, int pixel_format, b2ref_imageref window, int user_x, int user_y,
+                  const b2ref_box2i* rects, int n, const uint8_t* table768, int redraw_borders);
+
 /* ---- rectangle lists (gui/dplug/gui/boxlist.d) */
 int b2ref_tile_areas(const b2ref_box2i* areas, int n, int max_w, int max_h, b2ref_box2i* out, int cap);
 int b2ref_remove_overlapping_areas(b2ref_box2i* boxes, int n, b2ref_box2i* out, int cap);

@@ -68,6 +68,7 @@ def lib():
             "b2ref_gfx_compositor": (V, [V]), "b2ref_gfx_map": (V, [V, I]), "b2ref_gfx_output": (I, [V, C.POINTER(imageref)]),
             "b2ref_gfx_regenerate_mipmaps": (I, [V, C.POINTER(box2i), I]),
             "b2ref_gfx_composite_gui": (I, [V, C.POINTER(box2i), I]),
+            "b2ref_present": (I, [imageref, imageref, I, imageref, I, I, C.POINTER(box2i), I, V, I]),
             "b2ref_tile_areas": (I, [C.POINTER(box2i), I, I, I, C.POINTER(box2i), I]),
             "b2ref_remove_overlapping_areas": (I, [C.POINTER(box2i), I, C.POINTER(box2i), I]),
             "b2ref_bounding_box": (box2i, [C.POINTER(box2i), I]), "b2ref_have_no_overlap": (I, [C.POINTER(box2i), I]),
@@ -171,6 +172,17 @@ class Mipmap:
 
     def linearMipmapSample(self, level, x, y):
         return self._sample(self.l.b2ref_mip_linear_mipmap_sample, level, x, y, lvl_float=True)
+
+
+def present(composited, rendered, pixelFormat, window, userOrigin, rects, table=None, redrawBorders=False):
+    """doDraw stages E-H on host arrays ((h, w, 4) uint8); `rendered` and `window` are updated in place."""
+    def ref(a):
+        return imageref(a.shape[1], a.shape[0], a.strides[0], a.ctypes.data)
+    t = None if table is None else np.ascontiguousarray(table, dtype=np.uint8).reshape(768)
+    rc = lib().b2ref_present(ref(composited), ref(rendered), pixelFormat, ref(window), userOrigin[0], userOrigin[1], boxes(rects), len(rects),
+                             None if t is None else t.ctypes.data_as(C.c_void_p), 1 if redrawBorders else 0)
+    assert rc == 0
+    return window
 
 
 def default_params():
