@@ -84,6 +84,10 @@ SIGNATURES = {
     "b2pbr_graph_begin": (C.c_int, [C.c_void_p]),
     "b2pbr_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "b2pbr_graph_launch": (C.c_int, [C.c_void_p, C.c_int]),
+    "b2layer_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "b2layer_destroy": (None, [C.c_void_p]),
+    "b2layer_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(box2i), C.c_int]),
+    "b2pbr_draw_layer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(box2i), C.c_int, C.c_int]),
     "b2pbr_present": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(box2i), C.c_int, C.c_int]),
     "b2pbr_set_color_correction": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b2_lift_gamma_gain_contrast_table": (None, [C.POINTER(C.c_float), C.c_void_p]),

@@ -33,6 +33,36 @@ def _ref(arr):
     return _lib.imageref(arr.shape[1], arr.shape[0], arr.strides[0], arr.ctypes.data)
 
 
+class Layer:
+    """Device-resident cache of a widget's PBR render (UIBufferedElementPBR buffers / PBRBackgroundGUI maps)."""
+    DIFFUSE, DEPTH, MATERIAL, DIFFUSE_OPACITY, DEPTH_OPACITY, MATERIAL_OPACITY = range(6)
+    BLIT, BLEND = 0, 1
+
+    def __init__(self, w, h, withOpacity=True, device=0):
+        self._l = _lib.lib()
+        h_ = C.c_void_p()
+        _lib.check(self._l.b2layer_create(C.byref(h_), device, w, h, 1 if withOpacity else 0))
+        self._h, self.w, self.h = h_, w, h
+
+    def close(self):
+        if self._h:
+            self._l.b2layer_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, plane, image, rects=None):
+        dt = np.uint16 if plane == self.DEPTH else np.uint8
+        image = np.ascontiguousarray(image, dtype=dt)
+        if rects is None:
+            rects = [(0, 0, self.w, self.h)]
+        _lib.check(self._l.b2layer_upload(self._h, plane, image.ctypes.data_as(C.c_void_p), image.strides[0], _lib.boxes(rects), len(rects)))
+
+
 class PBRCompositor:
     """`PBRCompositor(device)`; owns the device twins of the maps GUIGraphics lends to compositeTile."""
 
@@ -207,6 +237,10 @@ class PBRCompositor:
 
     def graphLaunch(self, gid):
         _lib.check(self._l.b2pbr_graph_launch(self._h, gid))
+
+    def drawLayer(self, layer, x, y, dirtyRects, mode=Layer.BLEND):
+        """the widget's onDrawPBR on the device: blit (PBRBackgroundGUI) or opacity-masked blend (UIBufferedElementPBR)"""
+        _lib.check(self._l.b2pbr_draw_layer(self._h, layer._h, x, y, _lib.boxes(dirtyRects), len(dirtyRects), mode))
 
     # --- post-composite chain, GUIGraphics.doDraw stages E-H (graphics.d:825-868) ---------------------------
     def setColorCorrection(self, table):

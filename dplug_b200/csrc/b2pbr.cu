@@ -24,6 +24,7 @@ void launch_cubic_rgba(const DevLevel& dst, const DevLevel& src, Box r, cudaStre
 void launch_cubic_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
 void launch_copy_diffuse(const DevLevel& dst, const DevLevel& src, const Box* boxes, int n, int grid, cudaStream_t s);
 void launch_swizzle(const DevLevel& dst, const DevLevel& src, Box box, int pf, cudaStream_t s);
+void launch_layer(bool blend, const DevLevel* dst3, const DevLevel* src3, const DevLevel* op3, Box box, int px, int py, cudaStream_t s);
 void launch_present(const DevLevel& win, const DevLevel& src, Box box, int dx, int dy, int pf, const uint8_t* lut, cudaStream_t s);
 void launch_fill32(const DevLevel& win, uint32_t value, cudaStream_t s);
 void launch_pbr_exact(const PbrArgs& args, int gridBlocks, cudaStream_t stream);
@@ -332,6 +333,62 @@ int b2_host_unregister(void* ptr) {
     return B2_OK;
 }
 
+}  // extern "C"
+
+// ================================================================================================ b2layer
+struct b2layer {
+    int device = 0, w = 0, h = 0;
+    bool opacity = false;
+    DevLevel plane[6];   // diffuse RGBA, depth L16, material RGBA, then the three L8 opacity masks
+    uint8_t* alloc = nullptr;
+};
+static const int kLayerElem[6] = {4, 2, 4, 1, 1, 1};
+
+extern "C" {
+int b2layer_create(b2layer** out, int device, int w, int h, int with_opacity) {
+    if (!out || w <= 0 || h <= 0) return fail(B2_ERR_INVALID, "b2layer_create: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(B2_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)"); }
+    if (device < 0 || device >= ndev) return fail(B2_ERR_INVALID, "bad device index");
+    CU(cudaSetDevice(device));
+    b2layer* l = new b2layer();
+    l->device = device; l->w = w; l->h = h; l->opacity = with_opacity != 0;
+    const int n = with_opacity ? 6 : 3;
+    size_t total = 0, offs[6] = {0};
+    for (int k = 0; k < n; ++k) {
+        DevLevel& L = l->plane[k];
+        L.w = w; L.h = h; L.y0 = 0; L.rows = h;
+        L.pitch = (int)alignUp((size_t)w * kLayerElem[k], 128);
+        offs[k] = total;
+        total += alignUp((size_t)L.pitch * h, 256);
+    }
+    if (cudaMalloc((void**)&l->alloc, total) != cudaSuccess) { delete l; return fail(B2_ERR_CUDA, "b2layer_create: cudaMalloc failed"); }
+    cudaMemset(l->alloc, 0, total);
+    for (int k = 0; k < n; ++k) l->plane[k].base = l->alloc + offs[k];
+    *out = l;
+    return B2_OK;
+}
+void b2layer_destroy(b2layer* l) {
+    if (!l) return;
+    cudaSetDevice(l->device);
+    cudaDeviceSynchronize();
+    if (l->alloc) cudaFree(l->alloc);
+    delete l;
+}
+int b2layer_upload(b2layer* l, int plane, const void* host, size_t pitch, const b2_box2i* rects, int n) {
+    if (!l || !host || plane < 0 || plane >= (l->opacity ? 6 : 3) || (n > 0 && !rects)) return fail(B2_ERR_INVALID, "b2layer_upload: bad arguments");
+    CU(cudaSetDevice(l->device));
+    const DevLevel& L = l->plane[plane];
+    const int e = kLayerElem[plane];
+    for (int k = 0; k < n; ++k) {
+        const b2_box2i& r = rects[k];
+        if (!boxSorted(r) || r.min_x < 0 || r.min_y < 0 || r.max_x > l->w || r.max_y > l->h) return fail(B2_ERR_INVALID, "b2layer_upload: rectangle outside the layer");
+        if (boxEmpty(r)) continue;
+        CU(cudaMemcpy2D(L.base + (size_t)r.min_y * L.pitch + (size_t)r.min_x * e, (size_t)L.pitch,
+                        (const uint8_t*)host + (size_t)r.min_y * pitch + (size_t)r.min_x * e, pitch, (size_t)boxW(r) * e, (size_t)boxH(r), cudaMemcpyHostToDevice));
+    }
+    return B2_OK;
+}
 }  // extern "C"
 
 // ================================================================================================ b2pbr
@@ -1100,6 +1157,25 @@ int b2pbr_graph_launch(b2pbr* c, int graph_id) {
     if (!c || graph_id < 0 || graph_id >= (int)c->graphs.size() || !c->graphs[graph_id]) return fail(B2_ERR_INVALID, "graph_launch: bad id");
     CU(cudaGraphLaunch(c->graphs[graph_id], c->stream));
     c->launches += c->graphLaunches[graph_id];
+    return B2_OK;
+}
+
+int b2pbr_draw_layer(b2pbr* c, b2layer* l, int x, int y, const b2_box2i* rects, int n, int mode) {
+    if (!c || !c->diffuse || !l || (n > 0 && !rects) || (mode != B2_LAYER_BLIT && mode != B2_LAYER_BLEND)) return fail(B2_ERR_INVALID, "draw_layer: bad arguments");
+    if (mode == B2_LAYER_BLEND && !l->opacity) return fail(B2_ERR_INVALID, "draw_layer: this layer has no opacity masks");
+    if (l->device != c->device) return fail(B2_ERR_INVALID, "draw_layer: layer lives on another device");
+    if (x < 0 || y < 0 || x + l->w > c->W || y + l->h > c->H) return fail(B2_ERR_INVALID, "draw_layer: widget outside the UI");
+    CU(cudaSetDevice(c->device));
+    const DevLevel dst3[3] = {c->diffuse->levels[0], c->depth->levels[0], c->material->levels[0]};
+    for (int k = 0; k < n; ++k) {
+        const b2_box2i& r = rects[k];
+        if (!boxSorted(r) || r.min_x < 0 || r.min_y < 0 || r.max_x > l->w || r.max_y > l->h) return fail(B2_ERR_INVALID, "draw_layer: dirty rectangle outside the widget");
+        if (boxEmpty(r)) continue;
+        if (r.min_y + y < dst3[0].y0 || r.max_y + y > dst3[0].y0 + dst3[0].rows) return fail(B2_ERR_INVALID, "draw_layer: rectangle outside this band");
+        launch_layer(mode == B2_LAYER_BLEND, dst3, l->plane, l->plane + 3, toBox(r), x, y, c->stream);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
     return B2_OK;
 }
 

@@ -330,6 +330,52 @@ __global__ void __launch_bounds__(256) k_fill32(DevLevel win, uint32_t value) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Level-0 producers that are plain per-pixel work: a widget's cached PBR render is
+// written into the three maps for its dirty rectangles, either copied (PBRBackgroundGUI.onDrawPBR,
+// pbrwidgets/dplug/pbrwidgets/pbrbackgroundgui.d:147-162) or blended through per-map 8-bit opacity masks
+// (UIBufferedElementPBR.onDrawPBR, gui/dplug/gui/bufferedelement.d:118-131; blendWithAlpha,
+// graphics/dplug/graphics/draw.d:933-969; blendColor, graphics/dplug/graphics/color.d:453-526).
+__device__ __forceinline__ uint32_t blendRGBA(uint32_t fg, uint32_t bg, uint32_t a) {
+    // per channel (fg*alpha + bg*(255-alpha)) / 255 with the reference's multiply-shift division (color.d:465-475),
+    // exact for operands up to 255*255
+    const uint32_t ia = (~a) & 0xffu;
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t v = ((fg >> (8 * k)) & 0xffu) * a + ((bg >> (8 * k)) & 0xffu) * ia;
+        o |= ((v * 32897u) >> 23) << (8 * k);
+    }
+    return o;
+}
+__device__ __forceinline__ uint32_t blendL16(uint32_t fg, uint32_t bg, uint32_t a8) {
+    // color.d:522-526 with alpha16 = (alpha << 8) | alpha (draw.d:961): the products are 32-bit `int` in the
+    // reference and DO wrap for bright texels with high opacity; the wrap and the signed division are kept
+    const uint32_t a16 = (a8 << 8) | a8, ia16 = (~a16) & 0xffffu;
+    const int32_t sum = (int32_t)(fg * a16 + bg * ia16);
+    return (uint32_t)(sum / 65535) & 0xffffu;
+}
+
+template <bool BLEND>
+__global__ void __launch_bounds__(256) k_layer(DevLevel dD, DevLevel dZ, DevLevel dM, DevLevel sD, DevLevel sZ, DevLevel sM,
+                                              DevLevel oD, DevLevel oZ, DevLevel oM, Box box, int px, int py) {
+    const int i = box.minx + blockIdx.x * blockDim.x + threadIdx.x;   // widget coordinates
+    const int j = box.miny + blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= box.maxx || j >= box.maxy) return;
+    const int X = i + px, Y = j + py;                                 // UI coordinates
+    uint32_t* pd = rowPtrW<uint32_t>(dD, Y) + X;
+    uint16_t* pz = rowPtrW<uint16_t>(dZ, Y) + X;
+    uint32_t* pm = rowPtrW<uint32_t>(dM, Y) + X;
+    const uint32_t fd = __ldg(rowPtr<uint32_t>(sD, j) + i);
+    const uint32_t fz = __ldg(rowPtr<uint16_t>(sZ, j) + i);
+    const uint32_t fm = __ldg(rowPtr<uint32_t>(sM, j) + i);
+    if (!BLEND) { *pd = fd; *pz = (uint16_t)fz; *pm = fm; return; }
+    const uint32_t ad = __ldg(rowPtr<uint8_t>(oD, j) + i), az = __ldg(rowPtr<uint8_t>(oZ, j) + i), am = __ldg(rowPtr<uint8_t>(oM, j) + i);
+    if (ad) *pd = blendRGBA(fd, *pd, ad);          // alpha == 0: the destination is left alone (draw.d:952-954)
+    if (az) *pz = (uint16_t)blendL16(fz, *pz, az);
+    if (am) *pm = blendRGBA(fm, *pm, am);
+}
+
+// ------------------------------------------------------------------------------------------------
 static inline dim3 gridFor(int nx, int ny, dim3 block) { return dim3((nx + block.x - 1) / block.x, (ny + block.y - 1) / block.y); }
 
 void launch_box_rgba(const DevLevel& dst, const DevLevel& src, Box r, bool premul, cudaStream_t s) {
@@ -362,6 +408,12 @@ void launch_swizzle(const DevLevel& dst, const DevLevel& src, Box box, int pf, c
     k_swizzle<<<gridFor(box.maxx - box.minx, box.maxy - box.miny, block), block, 0, s>>>(dst, src, box, pf);
 }
 
+void launch_layer(bool blend, const DevLevel* dst3, const DevLevel* src3, const DevLevel* op3, Box box, int px, int py, cudaStream_t s) {
+    dim3 block(32, 8);
+    dim3 grid = gridFor(box.maxx - box.minx, box.maxy - box.miny, block);
+    if (blend) k_layer<true><<<grid, block, 0, s>>>(dst3[0], dst3[1], dst3[2], src3[0], src3[1], src3[2], op3[0], op3[1], op3[2], box, px, py);
+    else k_layer<false><<<grid, block, 0, s>>>(dst3[0], dst3[1], dst3[2], src3[0], src3[1], src3[2], src3[0], src3[1], src3[2], box, px, py);
+}
 void launch_present(const DevLevel& win, const DevLevel& src, Box box, int dx, int dy, int pf, const uint8_t* lut, cudaStream_t s) {
     dim3 block(32, 8);
     k_present<<<gridFor(box.maxx - box.minx, box.maxy - box.miny, block), block, 0, s>>>(win, src, box, dx, dy, pf, lut);

@@ -192,6 +192,25 @@ int b2pbr_band_rows(const b2pbr*, int map, int level, int* stored_lo, int* store
 int b2pbr_graph_begin(b2pbr*);
 int b2pbr_graph_end(b2pbr*, int* graph_id);
 int b2pbr_graph_launch(b2pbr*, int graph_id);
+/* SURVEY §8(f) rows 2 and 3 — data-parallel level-0 producers.  b2layer = device-resident cache of one widget's PBR
+ * render: the buffers UIBufferedElementPBR keeps (gui/dplug/gui/bufferedelement.d:69-116: diffuse RGBA, depth L16,
+ * material RGBA + one L8 opacity mask each) or the resized background maps of PBRBackgroundGUI
+ * (pbrwidgets/dplug/pbrwidgets/pbrbackgroundgui.d:122-145, no masks; the stb_image_resize2 resampling that fills
+ * them stays on the host). */
+typedef struct b2layer b2layer;
+enum { B2_LAYER_DIFFUSE = 0, B2_LAYER_DEPTH = 1, B2_LAYER_MATERIAL = 2,
+       B2_LAYER_DIFFUSE_OPACITY = 3, B2_LAYER_DEPTH_OPACITY = 4, B2_LAYER_MATERIAL_OPACITY = 5 };
+enum { B2_LAYER_BLIT = 0, B2_LAYER_BLEND = 1 };
+int b2layer_create(b2layer** out, int device, int w, int h, int with_opacity);
+void b2layer_destroy(b2layer*);
+/* host -> device for rectangles of one plane (B2_LAYER_*), when the widget re-rendered its cache */
+int b2layer_upload(b2layer*, int plane, const void* host, size_t host_pitch, const b2_box2i* rects, int n);
+/* the widget's onDrawPBR for `dirty_rects` (widget coordinates), widget placed at (x, y) of the UI: writes level 0 of
+ * the compositor's three maps.  B2_LAYER_BLIT = PBRBackgroundGUI.onDrawPBR (pbrbackgroundgui.d:147-162);
+ * B2_LAYER_BLEND = UIBufferedElementPBR.onDrawPBR (bufferedelement.d:118-131; blendWithAlpha draw.d:933-969;
+ * blendColor color.d:453-526, bit-exact incl. the 32-bit wrap of the L16 products). */
+int b2pbr_draw_layer(b2pbr*, b2layer*, int x, int y, const b2_box2i* dirty_rects, int n, int mode);
+
 /* SURVEY §8(f) row 1 — the post-composite per-pixel chain of GUIGraphics.doDraw, stages E-H (graphics.d:825-868),
  * fused into one pass over the composited twin: blit composited -> rendered, UIColorCorrection transfer tables
  * (pbrwidgets/dplug/pbrwidgets/colorcorrection.d:128-170), reorderComponents(pf) with alpha = 255

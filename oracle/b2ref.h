@@ -67,6 +67,11 @@ int b2ref_gfx_composite_gui(b2ref_gfx*, const b2ref_box2i* rects, int n);
 int b2ref_present(b2ref_imageref composited, b2ref_imageref rendered, int pixel_format, b2ref_imageref window, int user_x, int user_y,
                   const b2ref_box2i* rects, int n, const uint8_t* table768, int redraw_borders);
 
+/* ---- widget cache -> level-0 maps: blit (pbrbackgroundgui.d:147-162) or blendWithAlpha (bufferedelement.d:118-131) */
+int b2ref_draw_layer(b2ref_imageref dstD, b2ref_imageref dstZ, b2ref_imageref dstM, b2ref_imageref srcD, b2ref_imageref srcZ,
+                     b2ref_imageref srcM, b2ref_imageref opD, b2ref_imageref opZ, b2ref_imageref opM, int x, int y,
+                     const b2ref_box2i* rects, int n, int mode);
+
 /* ---- rectangle lists (gui/dplug/gui/boxlist.d) */
 int b2ref_tile_areas(const b2ref_box2i* areas, int n, int max_w, int max_h, b2ref_box2i* out, int cap);
 int b2ref_remove_overlapping_areas(b2ref_box2i* boxes, int n, b2ref_box2i* out, int cap);

@@ -73,3 +73,56 @@ extern "C" int b2ref_present(b2ref_imageref composited, b2ref_imageref rendered,
             memcpy(win.scanline(j) + r.minx, rend.scanline(j - user_y) + (r.minx - user_x), (size_t)r.width() * 4);
     return 0;
 }
+
+// ---------------------------------------------------------------- level-0 producers
+// blendColor(RGBA) — graphics/dplug/graphics/color.d:453-482 (version(LDC) branch: madd, *32897, >>23)
+static RGBA blendColorRGBA(RGBA fg, RGBA bg, uint8_t alpha) {
+    uint8_t invAlpha = (uint8_t)(~(int)alpha);
+    int32_t fgp, bgp;
+    memcpy(&fgp, &fg, 4); memcpy(&bgp, &bg, 4);
+    __m128i alphaMask = _mm_set1_epi32((invAlpha << 16) | alpha);
+    __m128i zero = _mm_setzero_si128();
+    __m128i colorMask = _mm_unpacklo_epi8(_mm_cvtsi32_si128(fgp), _mm_cvtsi32_si128(bgp));
+    colorMask = _mm_unpacklo_epi8(colorMask, zero);
+    __m128i product = _mm_madd_epi16(colorMask, alphaMask);
+    product = _mm_mullo_epi32(product, _mm_set1_epi32(32897));
+    product = _mm_srli_epi32(product, 23);
+    __m128i c = _mm_packus_epi16(_mm_packs_epi32(product, zero), zero);
+    int32_t r = _mm_cvtsi128_si32(c);
+    RGBA out;
+    memcpy(&out, &r, 4);
+    return out;
+}
+// blendColor(L16) — color.d:522-526: `int` products (they wrap for bright texels), signed division
+static L16 blendColorL16(L16 fg, L16 bg, uint16_t alpha) {
+    uint16_t inv = (uint16_t)(~(int)alpha);
+    int32_t sum = (int32_t)((uint32_t)fg.l * (uint32_t)alpha + (uint32_t)bg.l * (uint32_t)inv);
+    return L16{(uint16_t)(sum / 65535)};
+}
+
+// UIBufferedElementPBR.onDrawPBR blend loop (bufferedelement.d:118-131) / PBRBackgroundGUI.onDrawPBR blit
+// (pbrbackgroundgui.d:147-162).  dst* are the three level-0 maps, src* / op* the widget's cached buffers, the widget
+// sits at (x, y); rects are in widget coordinates.  mode 0 = blit, 1 = blendWithAlpha (draw.d:933-969).
+extern "C" int b2ref_draw_layer(b2ref_imageref dstD, b2ref_imageref dstZ, b2ref_imageref dstM, b2ref_imageref srcD, b2ref_imageref srcZ,
+                                b2ref_imageref srcM, b2ref_imageref opD, b2ref_imageref opZ, b2ref_imageref opM, int x, int y,
+                                const b2ref_box2i* rects, int n, int mode) {
+    auto rowp = [](const b2ref_imageref& im, int j) { return (uint8_t*)im.pixels + (size_t)j * im.pitch; };
+    for (int k = 0; k < n; ++k) {
+        const b2ref_box2i r = rects[k];
+        for (int j = r.min_y; j < r.max_y; ++j) {
+            RGBA* dd = (RGBA*)rowp(dstD, j + y) + x; L16* dz = (L16*)rowp(dstZ, j + y) + x; RGBA* dm = (RGBA*)rowp(dstM, j + y) + x;
+            const RGBA* sd = (const RGBA*)rowp(srcD, j); const L16* sz = (const L16*)rowp(srcZ, j); const RGBA* sm = (const RGBA*)rowp(srcM, j);
+            if (mode == 0) {
+                for (int i = r.min_x; i < r.max_x; ++i) { dd[i] = sd[i]; dz[i] = sz[i]; dm[i] = sm[i]; }
+                continue;
+            }
+            const uint8_t* ad = rowp(opD, j); const uint8_t* az = rowp(opZ, j); const uint8_t* am = rowp(opM, j);
+            for (int i = r.min_x; i < r.max_x; ++i) {
+                if (ad[i]) dd[i] = blendColorRGBA(sd[i], dd[i], ad[i]);
+                if (az[i]) dz[i] = blendColorL16(sz[i], dz[i], (uint16_t)((az[i] << 8) | az[i]));
+                if (am[i]) dm[i] = blendColorRGBA(sm[i], dm[i], am[i]);
+            }
+        }
+    }
+    return 0;
+}

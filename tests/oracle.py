@@ -68,6 +68,7 @@ def lib():
             "b2ref_gfx_compositor": (V, [V]), "b2ref_gfx_map": (V, [V, I]), "b2ref_gfx_output": (I, [V, C.POINTER(imageref)]),
             "b2ref_gfx_regenerate_mipmaps": (I, [V, C.POINTER(box2i), I]),
             "b2ref_gfx_composite_gui": (I, [V, C.POINTER(box2i), I]),
+            "b2ref_draw_layer": (I, [imageref] * 9 + [I, I, C.POINTER(box2i), I, I]),
             "b2ref_present": (I, [imageref, imageref, I, imageref, I, I, C.POINTER(box2i), I, V, I]),
             "b2ref_tile_areas": (I, [C.POINTER(box2i), I, I, I, C.POINTER(box2i), I]),
             "b2ref_remove_overlapping_areas": (I, [C.POINTER(box2i), I, C.POINTER(box2i), I]),
@@ -172,6 +173,15 @@ class Mipmap:
 
     def linearMipmapSample(self, level, x, y):
         return self._sample(self.l.b2ref_mip_linear_mipmap_sample, level, x, y, lvl_float=True)
+
+
+def draw_layer(dst, src, opacity, x, y, rects, mode):
+    """dst / src / opacity: (diffuse, depth, material) numpy triples; dst is updated in place."""
+    def ref(a):
+        return imageref(a.shape[1], a.shape[0], a.strides[0], a.ctypes.data)
+    op = opacity if opacity is not None else src
+    rc = lib().b2ref_draw_layer(*[ref(a) for a in dst], *[ref(a) for a in src], *[ref(a) for a in op], x, y, boxes(rects), len(rects), mode)
+    assert rc == 0
 
 
 def present(composited, rendered, pixelFormat, window, userOrigin, rects, table=None, redrawBorders=False):
