@@ -53,6 +53,8 @@ SIGNATURES = {
     "b2mip_generate_level": (C.c_int, [C.c_void_p, C.c_int, C.c_int, box2i]),
     "b2mip_generate_mipmaps": (C.c_int, [C.c_void_p, C.c_int]),
     "b2mip_generate_chain": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "b2mip_generate_levels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), box2i, C.POINTER(box2i)]),
+    "b2_set_mip_fusion": (C.c_int, [C.c_int]),
     "b2mip_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2mip_sync": (C.c_int, [C.c_void_p]),
     "b2mip_kernel_launches": (C.c_uint64, [C.c_void_p]),

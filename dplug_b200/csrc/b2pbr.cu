@@ -22,6 +22,8 @@ void launch_box_rgba(const DevLevel& dst, const DevLevel& src, Box r, bool premu
 void launch_box_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
 void launch_cubic_rgba(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
 void launch_cubic_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
+void launch_mip_fused(bool rgba, const FusedArgs& a, int tilesY, cudaStream_t s);
+int mip_fused_tile(int n);
 void launch_copy_diffuse(const DevLevel& dst, const DevLevel& src, const Box* boxes, int n, int grid, cudaStream_t s);
 void launch_swizzle(const DevLevel& dst, const DevLevel& src, Box box, int pf, cudaStream_t s);
 void launch_layer(bool blend, const DevLevel* dst3, const DevLevel* src3, const DevLevel* op3, Box box, int px, int py, cudaStream_t s);
@@ -169,6 +171,72 @@ static int mipGenerateLevel(b2mip* m, int level, int quality, b2_box2i r) {
     return B2_OK;
 }
 
+// ---- fused chain (mip_fused.cu).  `rects[k]` is the update rectangle of level first + k, `q[k]` the quality of the
+// step producing it; exactly the result of n successive mipGenerateLevel calls.
+static bool g_mipFusion = true;
+
+static bool mipWhole(const b2mip* m) {   // every level stores all of its rows (not a row band)
+    for (const DevLevel& L : m->levels)
+        if (L.y0 != 0 || L.rows != L.h) return false;
+    return true;
+}
+
+static int mipGenerateGroup(b2mip* m, int first, int n, const int* q, const b2_box2i* rects) {
+    FusedArgs a{};
+    a.n = n;
+    a.lv[0] = m->levels[first - 1];
+    const int last = first + n - 1;
+    const DevLevel& LL = m->levels[last];
+    const int tile = mip_fused_tile(n);
+    int tx0 = 1 << 30, ty0 = 1 << 30, tx1 = -1, ty1 = -1;
+    for (int k = 0; k < n; ++k) {
+        a.lv[k + 1] = m->levels[first + k];
+        a.q[k] = q[k];
+        if (m->color != B2_COLOR_RGBA8 && q[k] == B2_QUALITY_BOX_ALPHACOV_PREMUL)
+            return fail(B2_ERR_INVALID, "generateLevel: boxAlphaCovIntoPremul is RGBA-only (mipmap.d:594-595)");
+        if (q[k] < 0 || q[k] > 2) return fail(B2_ERR_INVALID, "generateLevel: unknown quality");
+        const b2_box2i& r = rects[k];
+        if (boxW(r) <= 0 || boxH(r) <= 0) { a.upd[k] = Box{0, 0, 0, 0}; continue; }   // a no-op in the reference
+        int rc = mipCheckRect(m, first + k, r, "generateLevel");
+        if (rc) return rc;
+        a.upd[k] = toBox(r);
+        // tiles of the last level owning a texel of this rectangle: its ancestors (the odd last column / row of a
+        // level belongs to the tile on the edge)
+        const int sh = n - 1 - k;
+        auto anc = [&](int v, int dim) { v >>= sh; return v < dim ? v : dim - 1; };
+        const int ax0 = anc(r.min_x, LL.w) / tile, ax1 = anc(r.max_x - 1, LL.w) / tile;
+        const int ay0 = anc(r.min_y, LL.h) / tile, ay1 = anc(r.max_y - 1, LL.h) / tile;
+        if (ax0 < tx0) tx0 = ax0;
+        if (ay0 < ty0) ty0 = ay0;
+        if (ax1 > tx1) tx1 = ax1;
+        if (ay1 > ty1) ty1 = ay1;
+    }
+    if (tx1 < 0) return B2_OK;   // nothing to regenerate
+    a.tile0x = tx0; a.tile0y = ty0; a.tilesX = tx1 - tx0 + 1;
+    CU(cudaSetDevice(m->device));
+    launch_mip_fused(m->color == B2_COLOR_RGBA8, a, ty1 - ty0 + 1, m->stream);
+    m->launches++;
+    CU(cudaGetLastError());
+    return B2_OK;
+}
+
+// levels first .. first + n - 1, in launches of up to three levels (or level by level for row bands / fusion off)
+static int mipGenerateLevels(b2mip* m, int first, int n, const int* q, const b2_box2i* rects) {
+    if (first < 1 || n < 0 || first + n > (int)m->levels.size()) return fail(B2_ERR_INVALID, "generateLevel: level out of range");
+    if (!g_mipFusion || !mipWhole(m)) {
+        for (int k = 0; k < n; ++k) {
+            int rc = mipGenerateLevel(m, first + k, q[k], rects[k]);
+            if (rc) return rc;
+        }
+        return B2_OK;
+    }
+    for (int k = 0; k < n; k += 3) {
+        int rc = mipGenerateGroup(m, first + k, n - k < 3 ? n - k : 3, q + k, rects + k);
+        if (rc) return rc;
+    }
+    return B2_OK;
+}
+
 extern "C" {
 
 const char* b2_last_error(void) { return g_err.c_str(); }
@@ -258,25 +326,40 @@ int b2mip_generate_next_level(b2mip* m, int quality, b2_box2i prev, int level, b
     if (out_rect) *out_rect = r;
     return mipGenerateLevel(m, level, quality, r);
 }
+int b2mip_generate_levels(b2mip* m, int first_level, int n, const int* qualities, b2_box2i prev, b2_box2i* out_rects) {
+    if (!m || n < 0 || (n > 0 && !qualities) || n > 32) return fail(B2_ERR_INVALID, "generate_levels: bad arguments");
+    if (first_level < 1 || first_level + n > (int)m->levels.size()) return fail(B2_ERR_INVALID, "generate_levels: level out of range");
+    b2_box2i rects[32];
+    for (int k = 0; k < n; ++k) {
+        const DevLevel& P = m->levels[first_level + k - 1];
+        prev = impactOnNextLevel(qualities[k], prev, P.w, P.h);
+        rects[k] = prev;
+        if (out_rects) out_rects[k] = prev;
+    }
+    return mipGenerateLevels(m, first_level, n, qualities, rects);
+}
 int b2mip_generate_mipmaps(b2mip* m, int quality) {
     if (!m) return fail(B2_ERR_INVALID, "null mip");
-    b2_box2i r{0, 0, m->W, m->H};
-    for (int level = 1; level < (int)m->levels.size(); ++level) {
+    int q[32];
+    const int n = (int)m->levels.size() - 1;
+    for (int level = 1; level <= n && level <= 32; ++level) {
         if (level >= 3 && quality == B2_QUALITY_BOX) quality = B2_QUALITY_CUBIC;  // mipmap.d:522-524
-        int rc = b2mip_generate_next_level(m, quality, r, level, &r);
-        if (rc) return rc;
+        q[level - 1] = quality;
     }
-    return B2_OK;
+    return b2mip_generate_levels(m, 1, n, q, b2_box2i{0, 0, m->W, m->H}, nullptr);
 }
 int b2mip_generate_chain(b2mip* m, int first_quality, int cubic_from_level) {
     if (!m) return fail(B2_ERR_INVALID, "null mip");
-    b2_box2i r{0, 0, m->W, m->H};
-    for (int level = 1; level < (int)m->levels.size(); ++level) {
-        int q = level >= cubic_from_level ? B2_QUALITY_CUBIC : (level == 1 ? first_quality : B2_QUALITY_BOX);
-        int rc = b2mip_generate_next_level(m, q, r, level, &r);
-        if (rc) return rc;
-    }
-    return B2_OK;
+    int q[32];
+    const int n = (int)m->levels.size() - 1;
+    for (int level = 1; level <= n && level <= 32; ++level)
+        q[level - 1] = level >= cubic_from_level ? B2_QUALITY_CUBIC : (level == 1 ? first_quality : B2_QUALITY_BOX);
+    return b2mip_generate_levels(m, 1, n, q, b2_box2i{0, 0, m->W, m->H}, nullptr);
+}
+int b2_set_mip_fusion(int enabled) {
+    const int was = g_mipFusion ? 1 : 0;
+    g_mipFusion = enabled != 0;
+    return was;
 }
 int b2mip_sample(b2mip* m, int kind, int n, const float* level, const float* x, const float* y, float* out4) {
     if (!m || n < 0 || kind < 0 || kind > 2) return fail(B2_ERR_INVALID, "b2mip_sample: bad arguments");
@@ -843,8 +926,18 @@ int b2pbr_regenerate_mipmaps(b2pbr* c, const b2_box2i* rects, int n) {
         c->depth->stream = c->sAux;
     }
     int err = B2_OK;
+    // one dirty rectangle on an unbanded canvas (the full-frame case, and most interactive redraws): the whole chain
+    // of a pyramid goes through the fused launches.  Several rectangles keep the reference's level-major order
+    // (graphics.d:1378-1419: all rectangles of a level before the next level), one launch per level and rectangle.
+    const bool fused = (n == 1) && !c->banded;
     traceBegin(c, "diffuse mipmap");
-    for (int level = 1; level < (int)c->diffuse->levels.size() && !err; ++level) {
+    if (fused) {
+        int q[kMaxDiffuseLevels];
+        const int nl = (int)c->diffuse->levels.size() - 1;
+        for (int level = 1; level <= nl; ++level) q[level - 1] = level == 1 ? B2_QUALITY_BOX_ALPHACOV_PREMUL : B2_QUALITY_CUBIC;
+        err = b2mip_generate_levels(c->diffuse, 1, nl, q, rects[0], nullptr);
+    }
+    for (int level = 1; !fused && level < (int)c->diffuse->levels.size() && !err; ++level) {
         int q = level == 1 ? B2_QUALITY_BOX_ALPHACOV_PREMUL : B2_QUALITY_CUBIC;  // graphics.d:1380-1384
         for (auto& area : s0) {
             const DevLevel& Pv = c->diffuse->levels[level - 1];
@@ -860,7 +953,13 @@ int b2pbr_regenerate_mipmaps(b2pbr* c, const b2_box2i* rects, int n) {
     traceEnd(c);
     // depth: replicateBordersTouching(area) (graphics.d:1406-1408) is clamp-to-edge addressing on the device
     traceBegin(c, "depth mipmap");
-    for (int level = 1; level < (int)c->depth->levels.size() && !err; ++level) {
+    if (fused && !err) {
+        int q[kMaxDepthLevels];
+        const int nl = (int)c->depth->levels.size() - 1;
+        for (int level = 1; level <= nl; ++level) q[level - 1] = level >= 3 ? B2_QUALITY_CUBIC : B2_QUALITY_BOX;
+        err = b2mip_generate_levels(c->depth, 1, nl, q, rects[0], nullptr);
+    }
+    for (int level = 1; !fused && level < (int)c->depth->levels.size() && !err; ++level) {
         int q = level >= 3 ? B2_QUALITY_CUBIC : B2_QUALITY_BOX;  // graphics.d:1414
         for (auto& area : s1) {
             const DevLevel& Pv = c->depth->levels[level - 1];

@@ -29,6 +29,15 @@ __device__ __forceinline__ T* rowPtrW(const DevLevel& L, int y) {
 
 struct Box { int minx, miny, maxx, maxy; };
 
+// One launch of the fused mipmap chain (mip_fused.cu): up to three consecutive generateLevel calls.
+struct FusedArgs {
+    DevLevel lv[4];   // source level s, then s+1 .. s+n
+    Box upd[3];       // update rectangle of level s+1+k (generateLevel's `updateRect`), possibly empty
+    int q[3];         // quality of the step producing level s+1+k (B2_QUALITY_*)
+    int n;            // steps in this launch, 1..3
+    int tile0x, tile0y, tilesX;   // first tile (in tiles of the last level) and tiles per grid row
+};
+
 constexpr int kMaxDiffuseLevels = 6;   // Mipmap(5): gui/dplug/gui/graphics.d:1118
 constexpr int kMaxDepthLevels = 5;     // Mipmap(4): graphics.d:1119
 constexpr int kMaxSkyLevels = 13;      // Mipmap(12): gui/dplug/gui/legacypbr.d:868

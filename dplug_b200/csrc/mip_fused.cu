@@ -1,0 +1,234 @@
+// Fused mipmap chain: up to THREE consecutive generateLevel calls (graphics/dplug/graphics/mipmap.d:534-618) in one
+// launch.  The level-by-level chain is bandwidth-wasteful on the GPU (every intermediate level is written to HBM and
+// read back by the next launch, and the small top levels are pure launch latency); here a CTA owns one tile of the
+// LAST level of the group, derives the regions of the intermediate levels that tile depends on (the [1 3 3 1] cubic
+// reaches one texel beyond its 2x2 children on each side), produces them in shared memory and writes to HBM only the
+// texels it owns.  The source level is read once (+ the halo a neighbouring CTA re-reads through L2).
+//
+// Semantics are EXACTLY those of the sequential chain on the same update rectangles: a texel of an intermediate
+// level is recomputed when it lies inside that level's update rectangle and is otherwise taken from the stored level
+// (what the next generateLevel call of the chain would read), so the result does not depend on the pyramid having
+// been consistent outside the rectangles.  All arithmetic is the per-level kernels' (mip_math.cuh): integer paths
+// bit-exact, the alpha-premultiplying box in single IEEE operations (this file is compiled with -fmad=false).
+#include "mip_math.cuh"
+
+namespace b2 {
+
+constexpr int Q_CUBIC = 1, Q_PREMUL = 2;   // B2_QUALITY_CUBIC, B2_QUALITY_BOX_ALPHACOV_PREMUL of include/b2pbr.h (0 = box)
+constexpr int FUSED_THREADS = 256;
+
+struct Iv { int a, b; };   // half-open interval of texel indices
+__device__ __forceinline__ bool inIv(Iv r, int v) { return v >= r.a && v < r.b; }
+__device__ __forceinline__ Iv ivUnion(Iv p, Iv q) { return Iv{min(p.a, q.a), max(p.b, q.b)}; }
+// texels of the finer level owned by the CTA that owns `up` of the coarser one: the 2x2 children, plus the odd last
+// column / row of the finer level (it has no parent, mipmap.d:119-125) for the tile touching the edge
+__device__ __forceinline__ Iv ivChildren(Iv up, int dimUp, int dimDown) { return Iv{2 * up.a, up.b == dimUp ? dimDown : 2 * up.b}; }
+// source texels read to produce `r` (mipmap.d:683-700 box: 2x, 2x+1; mipmap.d:906-935 cubic: 2x-1 .. 2x+2, clamped)
+__device__ __forceinline__ Iv ivNeed(int q, Iv r, int dimSrc) {
+    if (q == Q_CUBIC) return Iv{max(2 * r.a - 1, 0), min(2 * r.b + 1, dimSrc)};
+    return Iv{2 * r.a, 2 * r.b};
+}
+__device__ __forceinline__ bool inBox(const Box& b, int x, int y) { return x >= b.minx && x < b.maxx && y >= b.miny && y < b.maxy; }
+
+// a rectangle of one level held in shared memory: texel (x, y) of the level is p[(y - y0) * stride + (x - x0)]
+template <typename T>
+struct Region {
+    T* p; int x0, y0, stride;
+    __device__ __forceinline__ T& at(int x, int y) const { return p[(y - y0) * stride + (x - x0)]; }
+};
+template <typename T>
+struct GlobalSrc {
+    const DevLevel& L;
+    __device__ __forceinline__ uint32_t operator()(int x, int y) const { return rowPtr<T>(L, y)[x]; }
+};
+template <typename T>
+struct SharedSrc {
+    const Region<T>& R;
+    __device__ __forceinline__ uint32_t operator()(int x, int y) const { return R.at(x, y); }
+};
+
+// one destination texel of any quality from any source; (sw, sh) = source level size
+template <typename T, typename F>
+__device__ __forceinline__ uint32_t downTexel(int q, int x, int y, int sw, int sh, F fetch) {
+    if (q == Q_CUBIC) {
+        const int xs[4] = {max(2 * x - 1, 0), 2 * x, 2 * x + 1, min(2 * x + 2, sw - 1)};
+        const int ym = max(2 * y - 1, 0), yp = min(2 * y + 2, sh - 1);
+        if (sizeof(T) == 4) {
+            uint32_t lo[4], hi[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) vsumRGBA(fetch(xs[k], ym), fetch(xs[k], 2 * y), fetch(xs[k], 2 * y + 1), fetch(xs[k], yp), lo[k], hi[k]);
+            const uint32_t sl = lo[0] + 3u * lo[1] + 3u * lo[2] + lo[3] + 0x00200020u;
+            const uint32_t sh2 = hi[0] + 3u * hi[1] + 3u * hi[2] + hi[3] + 0x00200020u;
+            return ((sl >> 6) & 0x00ff00ffu) | (((sh2 >> 6) & 0x00ff00ffu) << 8);
+        } else {
+            uint32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = fetch(xs[k], ym) + 3u * fetch(xs[k], 2 * y) + 3u * fetch(xs[k], 2 * y + 1) + fetch(xs[k], yp);
+            return (v[0] + 3u * v[1] + 3u * v[2] + v[3] + 32u) >> 6;
+        }
+    }
+    const uint32_t a = fetch(2 * x, 2 * y), b = fetch(2 * x + 1, 2 * y), c = fetch(2 * x, 2 * y + 1), d = fetch(2 * x + 1, 2 * y + 1);
+    if (sizeof(T) == 4) return q == Q_PREMUL ? premul4(a, b, c, d) : box4(a, b, c, d);
+    return (a + b + c + d + 2u) >> 2;   // generateLevelBoxL16, mipmap.d:764-794
+}
+
+__device__ __forceinline__ uint32_t fastDiv(uint32_t v, uint32_t d, uint32_t magic) { return d == 1u ? v : __umulhi(v, magic); }
+
+// ---- step 1: global source level -> level s+1 (shared region `out` when another step follows, HBM for owned texels)
+template <typename T>
+__device__ __forceinline__ void stepFromGlobal(int q, const DevLevel& src, const DevLevel& dst, const Box& upd, Iv ownX, Iv ownY,
+                                               Iv compX, Iv compY, bool keep, const Region<T>& out) {
+    constexpr int G = sizeof(T) == 4 ? 2 : 4;   // destination texels per 128-bit source vector pair
+    const int gx0 = out.x0;                     // == compX.a rounded down to a multiple of G
+    const uint32_t ngx = (uint32_t)(compX.b - gx0 + G - 1) / G;
+    const uint32_t rows = (uint32_t)(compY.b - compY.a);
+    const uint32_t magic = 0xffffffffu / ngx + 1u;
+    const GlobalSrc<T> fetch{src};
+    for (uint32_t idx = threadIdx.x; idx < ngx * rows; idx += FUSED_THREADS) {
+        const uint32_t r = fastDiv(idx, ngx, magic);
+        const int y = compY.a + (int)r, x = gx0 + (int)(idx - r * ngx) * G;
+        const bool rowUpd = y >= upd.miny && y < upd.maxy;
+        if (q != Q_CUBIC && rowUpd && x >= upd.minx && x + G <= upd.maxx) {
+            // the whole group is recomputed: one 128-bit load per source row (2x + 2G - 1 <= src.w - 1 because x + G <= dst.w)
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(rowPtr<T>(src, 2 * y) + 2 * x));
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(rowPtr<T>(src, 2 * y + 1) + 2 * x));
+            uint2 o;
+            if (sizeof(T) == 4) {
+                if (q == Q_PREMUL) o = premul4x2(a.x, a.y, b.x, b.y, a.z, a.w, b.z, b.w);
+                else { o.x = box4(a.x, a.y, b.x, b.y); o.y = box4(a.z, a.w, b.z, b.w); }
+            } else {
+                o.x = boxL16pair(a.x, a.y, b.x, b.y);
+                o.y = boxL16pair(a.z, a.w, b.z, b.w);
+            }
+            if (keep) *reinterpret_cast<uint2*>(&out.at(x, y)) = o;
+            if (inIv(ownY, y)) {
+                T* d = rowPtrW<T>(dst, y);
+                if (x >= ownX.a && x + G <= ownX.b) *reinterpret_cast<uint2*>(d + x) = o;
+                else {
+#pragma unroll
+                    for (int t = 0; t < G; ++t) {
+                        const uint32_t v = sizeof(T) == 4 ? (t ? o.y : o.x) : (((t < 2 ? o.x : o.y) >> (16 * (t & 1))) & 0xffffu);
+                        if (inIv(ownX, x + t)) d[x + t] = (T)v;
+                    }
+                }
+            }
+        } else {
+            for (int t = 0; t < G; ++t) {
+                const int xx = x + t;
+                if (xx >= dst.w) break;
+                const bool isUpd = rowUpd && xx >= upd.minx && xx < upd.maxx;
+                uint32_t v;
+                if (isUpd) v = downTexel<T>(q, xx, y, src.w, src.h, fetch);
+                else v = rowPtr<T>(dst, y)[xx];                      // not regenerated: the stored texel is what the chain reads
+                if (keep) out.at(xx, y) = (T)v;
+                if (isUpd && inIv(ownX, xx) && inIv(ownY, y)) rowPtrW<T>(dst, y)[xx] = (T)v;
+            }
+        }
+    }
+}
+
+// ---- steps 2 and 3: shared region of level k-1 -> level k
+template <typename T>
+__device__ __forceinline__ void stepFromShared(int q, const Region<T>& in, int sw, int sh, const DevLevel& dst, const Box& upd, Iv ownX, Iv ownY,
+                                               Iv compX, Iv compY, bool keep, const Region<T>& out) {
+    const uint32_t ngx = (uint32_t)(compX.b - compX.a + 1) / 2;   // pairs of adjacent texels
+    const uint32_t rows = (uint32_t)(compY.b - compY.a);
+    const uint32_t magic = 0xffffffffu / ngx + 1u;
+    const SharedSrc<T> fetch{in};
+    for (uint32_t idx = threadIdx.x; idx < ngx * rows; idx += FUSED_THREADS) {
+        const uint32_t r = fastDiv(idx, ngx, magic);
+        const int y = compY.a + (int)r, x = compX.a + (int)(idx - r * ngx) * 2;
+        const bool rowUpd = y >= upd.miny && y < upd.maxy;
+        if (sizeof(T) == 4 && q == Q_CUBIC && rowUpd && x >= upd.minx && x + 2 <= upd.maxx && x + 2 <= compX.b && 2 * x - 1 >= 0 && 2 * x + 4 <= sw - 1) {
+            // two adjacent texels share four of their six source columns 2x-1 .. 2x+4 (no horizontal clamp in here)
+            const int ys[4] = {max(2 * y - 1, 0), 2 * y, 2 * y + 1, min(2 * y + 2, sh - 1)};
+            uint32_t c[6][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const T* row = &in.at(2 * x, ys[k]);                 // (2x - in.x0) is even: 64-bit aligned
+                const uint2 m = *reinterpret_cast<const uint2*>(row), p = *reinterpret_cast<const uint2*>(row + 2);
+                c[0][k] = row[-1]; c[1][k] = m.x; c[2][k] = m.y; c[3][k] = p.x; c[4][k] = p.y; c[5][k] = row[4];
+            }
+            uint32_t lo[6], hi[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) vsumRGBA(c[k][0], c[k][1], c[k][2], c[k][3], lo[k], hi[k]);
+            uint32_t o[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const uint32_t sl = lo[2 * t] + 3u * lo[2 * t + 1] + 3u * lo[2 * t + 2] + lo[2 * t + 3] + 0x00200020u;
+                const uint32_t sh2 = hi[2 * t] + 3u * hi[2 * t + 1] + 3u * hi[2 * t + 2] + hi[2 * t + 3] + 0x00200020u;
+                o[t] = ((sl >> 6) & 0x00ff00ffu) | (((sh2 >> 6) & 0x00ff00ffu) << 8);
+            }
+            if (keep) { out.at(x, y) = (T)o[0]; out.at(x + 1, y) = (T)o[1]; }
+            if (inIv(ownY, y)) {
+                T* d = rowPtrW<T>(dst, y);
+                if (inIv(ownX, x)) d[x] = (T)o[0];
+                if (inIv(ownX, x + 1)) d[x + 1] = (T)o[1];
+            }
+        } else {
+            for (int t = 0; t < 2; ++t) {
+                const int xx = x + t;
+                if (xx >= compX.b) break;
+                const bool isUpd = rowUpd && xx >= upd.minx && xx < upd.maxx;
+                uint32_t v;
+                if (isUpd) v = downTexel<T>(q, xx, y, sw, sh, fetch);
+                else v = rowPtr<T>(dst, y)[xx];
+                if (keep) out.at(xx, y) = (T)v;
+                if (isUpd && inIv(ownX, xx) && inIv(ownY, y)) rowPtrW<T>(dst, y)[xx] = (T)v;
+            }
+        }
+    }
+}
+
+// TW1 x TH1 = texels of level s+1 a CTA owns (before the odd-edge extension); the tile of the last level of an
+// N-step launch is (TW1 >> (N-1)) x (TH1 >> (N-1))
+template <typename T, int N, int TW1, int TH1>
+__global__ void __launch_bounds__(FUSED_THREADS) k_mip_fused(const __grid_constant__ FusedArgs A) {
+    constexpr int B1W = TW1 + 8, B1H = TH1 + 8, B2W = TW1 / 2 + 4, B2H = TH1 / 2 + 4;
+    __shared__ __align__(16) T buf1[N > 1 ? B1H * B1W : 8];
+    __shared__ __align__(16) T buf2[N > 2 ? B2H * B2W : 8];
+    const int tx = A.tile0x + (int)(blockIdx.x % (unsigned)A.tilesX), ty = A.tile0y + (int)(blockIdx.x / (unsigned)A.tilesX);
+    constexpr int tw = TW1 >> (N - 1), th = TH1 >> (N - 1);
+
+    // regions, from the last level down: own = texels this CTA writes, comp = texels it has to hold
+    Iv ownX[4], ownY[4], compX[4], compY[4];
+    ownX[N] = Iv{tx * tw, min((tx + 1) * tw, A.lv[N].w)};
+    ownY[N] = Iv{ty * th, min((ty + 1) * th, A.lv[N].h)};
+    compX[N] = ownX[N]; compY[N] = ownY[N];
+#pragma unroll
+    for (int k = N; k >= 2; --k) {
+        ownX[k - 1] = ivChildren(ownX[k], A.lv[k].w, A.lv[k - 1].w);
+        ownY[k - 1] = ivChildren(ownY[k], A.lv[k].h, A.lv[k - 1].h);
+        compX[k - 1] = ivUnion(ownX[k - 1], ivNeed(A.q[k - 1], compX[k], A.lv[k - 1].w));
+        compY[k - 1] = ivUnion(ownY[k - 1], ivNeed(A.q[k - 1], compY[k], A.lv[k - 1].h));
+    }
+    constexpr int G = sizeof(T) == 4 ? 2 : 4;
+    const Region<T> r1{buf1, compX[1].a & ~(G - 1), compY[1].a, B1W};
+    stepFromGlobal<T>(A.q[0], A.lv[0], A.lv[1], A.upd[0], ownX[1], ownY[1], compX[1], compY[1], N > 1, r1);
+    if (N >= 2) {
+        const Region<T> r2{buf2, compX[2].a & ~1, compY[2].a, B2W};
+        __syncthreads();
+        stepFromShared<T>(A.q[1], r1, A.lv[1].w, A.lv[1].h, A.lv[2], A.upd[1], ownX[2], ownY[2], compX[2], compY[2], N > 2, r2);
+        if (N >= 3) {
+            __syncthreads();
+            stepFromShared<T>(A.q[2], r2, A.lv[2].w, A.lv[2].h, A.lv[3], A.upd[2], ownX[3], ownY[3], compX[3], compY[3], false, r2);
+        }
+    }
+}
+
+constexpr int kTileW1 = 64, kTileH1 = 64;
+int mip_fused_tile(int n) { return kTileW1 >> (n - 1); }
+
+template <typename T>
+static void launchFusedT(const FusedArgs& a, int grid, cudaStream_t s) {
+    if (a.n == 1) k_mip_fused<T, 1, kTileW1, kTileH1><<<grid, FUSED_THREADS, 0, s>>>(a);
+    else if (a.n == 2) k_mip_fused<T, 2, kTileW1, kTileH1><<<grid, FUSED_THREADS, 0, s>>>(a);
+    else k_mip_fused<T, 3, kTileW1, kTileH1><<<grid, FUSED_THREADS, 0, s>>>(a);
+}
+void launch_mip_fused(bool rgba, const FusedArgs& a, int tilesY, cudaStream_t s) {
+    const int grid = a.tilesX * tilesY;
+    if (rgba) launchFusedT<uint32_t>(a, grid, s);
+    else launchFusedT<uint16_t>(a, grid, s);
+}
+
+}  // namespace b2

@@ -3,76 +3,9 @@
 // two (box) or four (cubic) source rows and writes one vector of destination texels; warps cover
 // contiguous row segments.  Integer paths are bit-exact by construction; the alpha-premultiplying box
 // is float but uses only IEEE * and + (this file is compiled with -fmad=false).
-#include "common.cuh"
+#include "mip_math.cuh"
 
 namespace b2 {
-
-// ------------------------------------------------------------------------------------------------
-// SIMD-in-register helpers: an RGBA8 texel is split into two 16-bit lanes pairs (r,b) and (g,a) so four
-// channels are summed with two integer adds; sums up to 64*255 fit the 16-bit lanes.
-__device__ __forceinline__ uint32_t evenBytes(uint32_t v) { return v & 0x00ff00ffu; }
-__device__ __forceinline__ uint32_t oddBytes(uint32_t v) { return (v >> 8) & 0x00ff00ffu; }
-
-// generateLevelBoxRGBA — mipmap.d:676-762: (a+b+c+d+2)>>2 per channel
-__device__ __forceinline__ uint32_t box4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    uint32_t lo = evenBytes(a) + evenBytes(b) + evenBytes(c) + evenBytes(d) + 0x00020002u;
-    uint32_t hi = oddBytes(a) + oddBytes(b) + oddBytes(c) + oddBytes(d) + 0x00020002u;
-    return ((lo >> 2) & 0x00ff00ffu) | (((hi >> 2) & 0x00ff00ffu) << 8);
-}
-
-// generateLevelBoxAlphaCovIntoPremulRGBA — mipmap.d:861-896 (non-legacy branch).
-//
-// The reference's arithmetic is a chain of single IEEE multiplies and adds per channel (no FMA).  Blackwell's packed
-// FP32 pipe (FFMA2: two independent fp32 lanes per instruction) evaluates two channels at once: a product is
-// fma(a, b, -0) and a sum is fma(a, 1, b) — each still ONE correctly rounded operation per lane, so the bytes are
-// the reference's.  Channels are paired (r, g) and (b, a).
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {   // exact rounded products
-    f32x2 r;
-    const f32x2 nz = 0x8000000080000000ull;                 // (-0, -0)
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
-    return r;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {   // exact rounded sums
-    f32x2 r;
-    const f32x2 one = 0x3f8000003f800000ull;                // (1, 1)
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(one), "l"(b));
-    return r;
-}
-struct Premul2 { f32x2 rg, ba; };
-__device__ __forceinline__ Premul2 premulLinear(uint32_t p) {   // convert_gammaspace_to_linear_premul, mipmap.d:869-878
-    const float invf = 1.0f / 255;
-    const f32x2 inv = pack2(invf, invf);
-    const f32x2 magic = pack2(-8388608.0f, -8388608.0f);
-    // byte -> float without I2F: (0x4B000000 | b) is the float 2^23 + b; the subtraction is exact
-    f32x2 rg = add2(pack2(__uint_as_float(__byte_perm(p, 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7441))), magic);
-    f32x2 ba = add2(pack2(__uint_as_float(__byte_perm(p, 0x4B000000u, 0x7442)), __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7443))), magic);
-    float fb, fa;
-    unpack2(ba, fb, fa);
-    const float al = fa * invf;                                  // res.a = col.a * inv_255
-    const f32x2 al2 = pack2(al, al);
-    f32x2 t = mul2(mul2(mul2(rg, inv), rg), inv);                // ((c * inv) * c) * inv
-    Premul2 o;
-    o.rg = mul2(t, al2);                                         // ... * res.a
-    float lb = fb * invf * fb * invf * al;
-    o.ba = pack2(lb, al);
-    return o;
-}
-__device__ __forceinline__ uint32_t premul4(uint32_t A, uint32_t B, uint32_t C, uint32_t D) {
-    Premul2 a = premulLinear(A), b = premulLinear(B), c = premulLinear(C), d = premulLinear(D);
-    f32x2 rg = add2(add2(add2(a.rg, b.rg), c.rg), d.rg);         // ((A + B) + C) + D, mipmap.d:886-889
-    f32x2 ba = add2(add2(add2(a.ba, b.ba), c.ba), d.ba);
-    const f32x2 q = pack2(0.25f, 0.25f), s255 = pack2(255.0f, 255.0f), h = pack2(0.5f, 0.5f);
-    rg = add2(mul2(mul2(rg, q), s255), h);                       // mean * 0.25f * 255.0f + 0.5f, mipmap.d:891-894
-    ba = add2(mul2(mul2(ba, q), s255), h);
-    float r_, g_, b_, a_;
-    unpack2(rg, r_, g_); unpack2(ba, b_, a_);
-    uint32_t ur = (uint32_t)__float2int_rz(r_) & 0xff, ug = (uint32_t)__float2int_rz(g_) & 0xff;
-    uint32_t ub = (uint32_t)__float2int_rz(b_) & 0xff, ua = (uint32_t)__float2int_rz(a_) & 0xff;
-    return ur | (ug << 8) | (ub << 16) | (ua << 24);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Box kernels.  Thread = 2 destination texels (x even) when the pair is inside the rectangle: one 128-bit
@@ -91,7 +24,7 @@ __global__ void __launch_bounds__(256) k_box_rgba(DevLevel dst, DevLevel src, Bo
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(s0 + 2 * x));
         const uint4 b = __ldg(reinterpret_cast<const uint4*>(s1 + 2 * x));
         uint2 o;
-        if (PREMUL) { o.x = premul4(a.x, a.y, b.x, b.y); o.y = premul4(a.z, a.w, b.z, b.w); }
+        if (PREMUL) o = premul4x2(a.x, a.y, b.x, b.y, a.z, a.w, b.z, b.w);
         else { o.x = box4(a.x, a.y, b.x, b.y); o.y = box4(a.z, a.w, b.z, b.w); }
         *reinterpret_cast<uint2*>(d + x) = o;
     } else {
@@ -105,11 +38,6 @@ __global__ void __launch_bounds__(256) k_box_rgba(DevLevel dst, DevLevel src, Bo
 
 // generateLevelBoxL16 — mipmap.d:764-794.  Thread = 4 destination texels: 128-bit load per source row
 // (8 x u16), 64-bit store.
-__device__ __forceinline__ uint32_t boxL16pair(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
-    uint32_t lo = ((a0 & 0xffffu) + (a0 >> 16) + (b0 & 0xffffu) + (b0 >> 16) + 2u) >> 2;
-    uint32_t hi = ((a1 & 0xffffu) + (a1 >> 16) + (b1 & 0xffffu) + (b1 >> 16) + 2u) >> 2;
-    return lo | (hi << 16);
-}
 __global__ void __launch_bounds__(256) k_box_l16(DevLevel dst, DevLevel src, Box r) {
     const int xq = (r.minx >> 2) + blockIdx.x * blockDim.x + threadIdx.x;  // quad index, absolute
     const int y = r.miny + blockIdx.y * blockDim.y + threadIdx.y;
@@ -143,10 +71,6 @@ __global__ void __launch_bounds__(256) k_box_l16(DevLevel dst, DevLevel src, Box
 // 128-bit vector 2x..2x+3 is loaded by the thread itself; column 2x-1 is the last texel of the left
 // neighbour lane's vector and column 2x+4 the first texel of the right neighbour's (warp shuffles); only
 // lanes on a warp / image edge issue an extra scalar load.
-__device__ __forceinline__ void vsumRGBA(uint32_t m1, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t& lo, uint32_t& hi) {
-    lo = evenBytes(m1) + 3u * evenBytes(p0) + 3u * evenBytes(p1) + evenBytes(p2);  // <= 8*255 per lane
-    hi = oddBytes(m1) + 3u * oddBytes(p0) + 3u * oddBytes(p1) + oddBytes(p2);
-}
 
 __global__ void __launch_bounds__(256) k_cubic_rgba(DevLevel dst, DevLevel src, Box r) {
     const int xp = (r.minx >> 1) + blockIdx.x * blockDim.x + threadIdx.x;

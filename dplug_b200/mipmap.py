@@ -124,6 +124,14 @@ class Mipmap:
     def generateChain(self, firstQuality, cubicFromLevel):
         _lib.check(self._l.b2mip_generate_chain(self._h, int(firstQuality), int(cubicFromLevel)))
 
+    def generateLevels(self, firstLevel, qualities, updateRectPreviousLevel):
+        """len(qualities) successive generateNextLevel calls in fused launches; returns the updated rectangles."""
+        n = len(qualities)
+        q = (C.c_int * max(n, 1))(*[int(v) for v in qualities])
+        out = (_lib.box2i * max(n, 1))()
+        _lib.check(self._l.b2mip_generate_levels(self._h, int(firstLevel), n, q, _lib.box2i(*updateRectPreviousLevel), out))
+        return [out[k].astuple() for k in range(n)]
+
     def _sample(self, kind, level, x, y):
         level = np.ascontiguousarray(np.broadcast_to(np.asarray(level, dtype=np.float32), np.shape(x)), dtype=np.float32).ravel()
         x = np.ascontiguousarray(x, dtype=np.float32).ravel()

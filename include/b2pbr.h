@@ -92,6 +92,15 @@ int b2mip_generate_mipmaps(b2mip*, int quality);
  * cubic — gui/dplug/gui/graphics.d:1378-1392; depth recipe: levels 1,2 box, >= 3 cubic — graphics.d:1412-1419).
  * Same results as the level-by-level chain over the full rectangle. */
 int b2mip_generate_chain(b2mip*, int first_quality, int cubic_from_level);
+/* `n` successive generateNextLevel calls — levels first_level .. first_level + n - 1 with qualities[k], the update
+ * rectangle propagated by impactOnNextLevel from `update_rect_previous_level` (what GUIGraphics.regenerateMipmaps does
+ * per dirty rectangle, graphics.d:1378-1419) — executed in launches of up to three levels that keep the intermediate
+ * levels in shared memory.  Bit-identical to the level-by-level chain, including when the stored levels are stale
+ * outside the rectangles.  out_rects (optional) receives the n updated rectangles. */
+int b2mip_generate_levels(b2mip*, int first_level, int n, const int* qualities, b2_box2i update_rect_previous_level,
+                          b2_box2i* out_rects);
+/* tuning / debugging knob (process-wide): 0 = every generateLevel is its own launch; returns the previous setting */
+int b2_set_mip_fusion(int enabled);
 /* the three samplers, evaluated on the device for `n` query points (test hook for mipmap.d:149-496) */
 int b2mip_sample(b2mip*, int kind /*0 linear,1 cubic,2 linearMipmap*/, int n, const float* level, const float* x,
                  const float* y, float* out4);

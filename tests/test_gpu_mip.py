@@ -50,6 +50,46 @@ def test_generate_next_level_dirty_rects(b2, oracle, color, quality):
         assert np.array_equal(g.download(1), o.download(1)), r
 
 
+def test_premul_box_rounding_known_answer(b2, oracle):
+    """A 2x2 quad whose green mean lands exactly on x.5 before the +0.5: ((A+B)+C)+D of singly rounded products gives
+    43, a fused multiply-add anywhere in the chain (or another summation order) gives 42.  Found by the fused-chain
+    tests; the expected bytes are the reference's arithmetic (mipmap.d:869-894) evaluated in numpy float32."""
+    quad = np.array([[[117, 203, 90, 151], [252, 120, 196, 176]], [[233, 153, 28, 71], [115, 55, 0, 210]]], dtype=np.uint8)
+    f = np.float32
+    inv = f(1.0) / f(255.0)
+    lin = np.zeros((4, 4), dtype=np.float32)
+    for t, p in enumerate(quad.reshape(4, 4)):
+        a = f(p[3]) * inv
+        for k in range(3):
+            lin[t, k] = f(p[k]) * inv * f(p[k]) * inv * a
+        lin[t, 3] = a
+    expect = [int(((lin[0, k] + lin[1, k]) + lin[2, k] + lin[3, k]) * f(0.25) * f(255.0) + f(0.5)) for k in range(4)]
+    assert expect == [76, 43, 31, 152]
+    # the quad at several positions (vector path, ragged edges) of a larger image
+    img = np.tile(quad, (9, 11, 1))
+    h, w = img.shape[:2]
+    for x0 in (0, 1):
+        g, o = b2.Mipmap(0, 1, w, h), oracle.Mipmap(0, 1, w, h)
+        g.upload(0, img); o.upload(0, img)
+        blank = np.zeros((h // 2, w // 2, 4), dtype=np.uint8)
+        g.upload(1, blank); o.upload(1, blank)
+        g.generateNextLevel(2, (2 * x0, 0, w, h), 1); o.generateNextLevel(2, (2 * x0, 0, w, h), 1)
+        out = g.download(1)
+        assert np.array_equal(out, o.download(1))
+        assert (out[:, x0:] == np.array(expect, dtype=np.uint8)).all()
+
+
+def test_premul_box_large_random(b2, oracle):
+    """2 M random quads against the oracle (rounding-boundary cases occur about once per 10^4 texels)."""
+    rng = np.random.default_rng(123)
+    w, h = 4096, 2048
+    img = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+    g, o = b2.Mipmap(0, 1, w, h), oracle.Mipmap(0, 1, w, h)
+    g.upload(0, img); o.upload(0, img)
+    g.generateNextLevel(2, (0, 0, w, h), 1); o.generateNextLevel(2, (0, 0, w, h), 1)
+    assert np.array_equal(g.download(1), o.download(1))
+
+
 def test_full_chain_diffuse_and_depth_recipes(b2, oracle):
     """regenerateMipmaps' recipes (graphics.d:1378-1419) level by level at the C1 size, odd dimensions included."""
     rng = np.random.default_rng(5)

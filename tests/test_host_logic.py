@@ -56,6 +56,24 @@ def test_product_does_not_link_oracle():
                 assert "b2ref" not in text and "oracle/" not in text.replace("oracle/rsqrtss_table.inc", ""), (dirpath, f)
 
 
+def test_exact_mip_kernels_contain_no_fused_multiply_add(b2):
+    """The alpha-premultiplying box must be a chain of single IEEE multiplies and adds (mipmap.d:869-894).  ptxas
+    (CUDA 12.9) contracts a packed FMUL2 feeding a packed FADD2 into FFMA2 even with explicit .rn and -fmad=false
+    (dplug_b200/csrc/mip_math.cuh explains the rule that avoids it); the built objects must hold no FFMA at all."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    for obj in ("mip_kernels.o", "mip_fused.o"):
+        path = os.path.join(ROOT, "dplug_b200", "build", obj)
+        if not os.path.exists(path):
+            pytest.skip("objects not kept (library built elsewhere)")
+        sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
+        fused = [ln.strip() for ln in sass.splitlines() if re.search(r"\bFFMA2?\b", ln)]
+        assert not fused, (obj, fused[:3])
+        assert "FMUL2" in sass or obj != "mip_kernels.o"   # the packed pipe is actually used
+
+
 def test_remove_overlapping_areas_known_answer(b2):
     # gui/dplug/gui/boxlist.d:120-135
     assert b2.removeOverlappingAreas([(0, 0, 4, 4), (2, 2, 6, 6), (1, 1, 2, 2)]) == [(2, 2, 6, 6), (0, 0, 4, 2), (0, 2, 2, 4)]
