@@ -159,7 +159,8 @@ def run_b200(args, W, H, desc):
     import numpy as np
     import torch
     import dplug_b200 as b2
-    from dplug_b200 import synth
+    from dplug_b200 import synth, _lib
+    _lib.lib().b2_set_mip_fusion(args.mip_fusion)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -324,46 +325,77 @@ def _peak():
 
 def run_c3(args, W, H, desc):
     """BASELINE config 3: the diffuse (emissive) pyramid recipe on one 8192x8192 RGBA image: level 1
-    boxAlphaCovIntoPremul, levels 2..8 cubic (graphics.d:1378-1392 with Mipmap(8))."""
+    boxAlphaCovIntoPremul, levels 2..8 cubic (graphics.d:1378-1392 with Mipmap(8)).  Headline = uniformly random
+    texels (alpha random: the worst case for the alpha-premultiplying box, no texel takes the alpha == 0 shortcut);
+    `variants.survey_diffuse` = the SURVEY section 8d diffuse map (emissive alpha on ~2 % of the area)."""
     import numpy as np
     import torch
     import dplug_b200 as b2
+    from dplug_b200 import _lib, synth
     torch.cuda.set_device(0)
     stream = torch.cuda.Stream()
+    _lib.lib().b2_set_mip_fusion(args.mip_fusion)
     R = 2   # two images (2 x 358 MB) alternate so the source is not L2-resident
-    rng = np.random.default_rng(1)
-    base = rng.integers(0, 256, size=(H // 8, W, 4), dtype=np.uint8)
-    mips = []
-    for k in range(R):
-        m = b2.Mipmap(b2.RGBA8, 8, W, H)
-        m.set_stream(stream.cuda_stream)
-        for b in range(8):
-            m.uploadRows(0, np.roll(base, k * 7 + b, axis=0), b * (H // 8))
-        mips.append(m)
-    for i in range(max(3, args.warmup)):
-        mips[i % R].generateChain(2, 2)
-    torch.cuda.synchronize()
-    l0 = sum(m.kernelLaunches() for m in mips)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(0); sampler.start(); time.sleep(0.3)
-    e0.record(stream)
-    for i in range(args.steps):
-        mips[i % R].generateChain(2, 2)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
     B = 4 * W * H + 4 * sum((W >> l) * (H >> l) for l in range(1, 9))
     peak, src = _peak()
+
+    def measure(fill):
+        mips = []
+        for k in range(R):
+            m = b2.Mipmap(b2.RGBA8, 8, W, H)
+            m.set_stream(stream.cuda_stream)
+            fill(m, k)
+            mips.append(m)
+        for i in range(max(3, args.warmup)):
+            mips[i % R].generateChain(2, 2)
+        torch.cuda.synchronize()
+        l0 = sum(m.kernelLaunches() for m in mips)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(0); sampler.start(); time.sleep(0.3)
+        e0.record(stream)
+        for i in range(args.steps):
+            mips[i % R].generateChain(2, 2)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        launches = int(sum(m.kernelLaunches() for m in mips) - l0)
+        del mips
+        return ms, clocks, launches
+
+    rng = np.random.default_rng(1)
+    base = rng.integers(0, 256, size=(H // 8, W, 4), dtype=np.uint8)
+
+    def fill_random(m, k):
+        for b in range(8):
+            m.uploadRows(0, np.roll(base, k * 7 + b, axis=0), b * (H // 8))
+
+    def fill_survey(m, k):
+        rows = 512
+        for y0 in range(0, H, rows):
+            m.uploadRows(0, synth.diffuse(W, H, seed=synth.SEED + k, y0=y0, y1=min(H, y0 + rows)), y0)
+
+    if args.c3_data == "survey":   # profiling aid: only the SURVEY data set
+        ms, clocks, launches = measure(fill_survey)
+        print(json.dumps({"workload": "c3", "texels": "survey", "ms_per_step": ms / args.steps, "gpu_launches": launches}), flush=True)
+        return
+    ms, clocks, launches = measure(fill_random)
+    ms2 = ms if args.c3_data == "random" else measure(fill_survey)[0]
     achieved = B * args.steps / (ms * 1e-3) / 1e9
+    achieved2 = B * args.steps / (ms2 * 1e-3) / 1e9
+    fused = args.mip_fusion
     print(json.dumps({
         "metric": "pyramid L0-Mpix/s (8-level emissive Mipmap chain)", "value": W * H * args.steps / (ms * 1e-3) / 1e6, "unit": "Mpix/s",
         "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": desc, "l2": "inputs larger than L2: %d images alternate (%.0f MB each)" % (R, B / 1e6)},
-        "roofline": {"bound": "hbm", "kernel": "mip chain (k_box_rgba<premul> + 7 x k_cubic_rgba)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": src, "algorithmic_bytes_per_launch": B},
-        "gpu_launches": int(sum(m.kernelLaunches() for m in mips) - l0), "clocks": clocks}), flush=True)
+        "config": {"workload": desc, "texels": "uniformly random RGBA (random alpha: worst case of the premultiplying box)",
+                   "mip_fusion": fused, "l2": "inputs larger than L2: %d images alternate (%.0f MB each)" % (R, B / 1e6)},
+        "roofline": {"bound": "hbm", "kernel": {0: "mip chain (k_box_rgba<premul> + 7 x k_cubic_rgba)", 1: "mip chain (k_box_rgba<premul>, 2 x k_cubic_rgba, k_mip_fused levels 4-6 and 7-8)", 2: "k_mip_fused x 3 (levels 1-3, 4-6, 7-8)"}[fused],
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": src,
+                     "algorithmic_bytes_per_launch": B},
+        "variants": {"survey_diffuse": {"texels": "SURVEY 8d diffuse map (emissive alpha on ~2 % of the area)", "ms_per_step": ms2 / args.steps,
+                                        "value": W * H * args.steps / (ms2 * 1e-3) / 1e6, "achieved": achieved2, "frac": achieved2 / peak}},
+        "gpu_launches": launches, "clocks": clocks}), flush=True)
 
 
 def run_c5(args, W, H, desc):
@@ -460,6 +492,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--instances", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c3-data", default="both", choices=["both", "random", "survey"])
+    ap.add_argument("--mip-fusion", type=int, default=1, choices=[0, 1, 2],
+                    help="0: one launch per generateLevel call; 1 (default): small levels fused; 2: every level fused")
     ap.add_argument("--graph", type=int, default=1, help="replay each frame's device work from a CUDA graph (1) or launch kernel by kernel (0)")
     args = ap.parse_args()
     W, H, desc = WORKLOADS[args.workload]

@@ -22,8 +22,9 @@ void launch_box_rgba(const DevLevel& dst, const DevLevel& src, Box r, bool premu
 void launch_box_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
 void launch_cubic_rgba(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
 void launch_cubic_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
-void launch_mip_fused(bool rgba, const FusedArgs& a, int tilesY, cudaStream_t s);
-int mip_fused_tile(int n);
+void launch_mip_fused(bool rgba, int variant, const FusedArgs& a, int tilesY, cudaStream_t s);
+int mip_fused_tile(int n, int variant);
+void mip_fused_variants(int q0, int out[2]);
 void launch_copy_diffuse(const DevLevel& dst, const DevLevel& src, const Box* boxes, int n, int grid, cudaStream_t s);
 void launch_swizzle(const DevLevel& dst, const DevLevel& src, Box box, int pf, cudaStream_t s);
 void launch_layer(bool blend, const DevLevel* dst3, const DevLevel* src3, const DevLevel* op3, Box box, int px, int py, cudaStream_t s);
@@ -174,6 +175,7 @@ static int mipGenerateLevel(b2mip* m, int level, int quality, b2_box2i r) {
 // ---- fused chain (mip_fused.cu).  `rects[k]` is the update rectangle of level first + k, `q[k]` the quality of the
 // step producing it; exactly the result of n successive mipGenerateLevel calls.
 static bool g_mipFusion = true;
+static long long g_mipFuseBelow = 1ll << 20;   // source levels up to this many texels start a fused group
 
 static bool mipWhole(const b2mip* m) {   // every level stores all of its rows (not a row band)
     for (const DevLevel& L : m->levels)
@@ -187,8 +189,6 @@ static int mipGenerateGroup(b2mip* m, int first, int n, const int* q, const b2_b
     a.lv[0] = m->levels[first - 1];
     const int last = first + n - 1;
     const DevLevel& LL = m->levels[last];
-    const int tile = mip_fused_tile(n);
-    int tx0 = 1 << 30, ty0 = 1 << 30, tx1 = -1, ty1 = -1;
     for (int k = 0; k < n; ++k) {
         a.lv[k + 1] = m->levels[first + k];
         a.q[k] = q[k];
@@ -197,24 +197,35 @@ static int mipGenerateGroup(b2mip* m, int first, int n, const int* q, const b2_b
         if (q[k] < 0 || q[k] > 2) return fail(B2_ERR_INVALID, "generateLevel: unknown quality");
         const b2_box2i& r = rects[k];
         if (boxW(r) <= 0 || boxH(r) <= 0) { a.upd[k] = Box{0, 0, 0, 0}; continue; }   // a no-op in the reference
-        int rc = mipCheckRect(m, first + k, r, "generateLevel");
-        if (rc) return rc;
+        if (int rc = mipCheckRect(m, first + k, r, "generateLevel")) return rc;
         a.upd[k] = toBox(r);
-        // tiles of the last level owning a texel of this rectangle: its ancestors (the odd last column / row of a
-        // level belongs to the tile on the edge)
-        const int sh = n - 1 - k;
-        auto anc = [&](int v, int dim) { v >>= sh; return v < dim ? v : dim - 1; };
-        const int ax0 = anc(r.min_x, LL.w) / tile, ax1 = anc(r.max_x - 1, LL.w) / tile;
-        const int ay0 = anc(r.min_y, LL.h) / tile, ay1 = anc(r.max_y - 1, LL.h) / tile;
-        if (ax0 < tx0) tx0 = ax0;
-        if (ay0 < ty0) ty0 = ay0;
-        if (ax1 > tx1) tx1 = ax1;
-        if (ay1 > ty1) ty1 = ay1;
+    }
+    // tiles of the last level owning a texel of some rectangle: the rectangles' ancestors (the odd last column / row
+    // of a level belongs to the tile on the edge).  Few large tiles -> small tiles (more CTAs).
+    int tile = 0, tx0 = 0, ty0 = 0, tx1 = -1, ty1 = -1, variant = 0, variants[2];
+    mip_fused_variants(q[0], variants);
+    for (int pass = 0; pass < 2; ++pass) {
+        variant = variants[pass];
+        tile = mip_fused_tile(n, variant);
+        tx0 = ty0 = 1 << 30; tx1 = ty1 = -1;
+        for (int k = 0; k < n; ++k) {
+            const b2_box2i& r = rects[k];
+            if (boxW(r) <= 0 || boxH(r) <= 0) continue;
+            const int sh = n - 1 - k;
+            auto anc = [&](int v, int dim) { v >>= sh; return v < dim ? v : dim - 1; };
+            const int ax0 = anc(r.min_x, LL.w) / tile, ax1 = anc(r.max_x - 1, LL.w) / tile;
+            const int ay0 = anc(r.min_y, LL.h) / tile, ay1 = anc(r.max_y - 1, LL.h) / tile;
+            if (ax0 < tx0) tx0 = ax0;
+            if (ay0 < ty0) ty0 = ay0;
+            if (ax1 > tx1) tx1 = ax1;
+            if (ay1 > ty1) ty1 = ay1;
+        }
+        if (tx1 < 0 || (long long)(tx1 - tx0 + 1) * (ty1 - ty0 + 1) >= 2 * 148) break;
     }
     if (tx1 < 0) return B2_OK;   // nothing to regenerate
     a.tile0x = tx0; a.tile0y = ty0; a.tilesX = tx1 - tx0 + 1;
     CU(cudaSetDevice(m->device));
-    launch_mip_fused(m->color == B2_COLOR_RGBA8, a, ty1 - ty0 + 1, m->stream);
+    launch_mip_fused(m->color == B2_COLOR_RGBA8, variant, a, ty1 - ty0 + 1, m->stream);
     m->launches++;
     CU(cudaGetLastError());
     return B2_OK;
@@ -230,9 +241,21 @@ static int mipGenerateLevels(b2mip* m, int first, int n, const int* q, const b2_
         }
         return B2_OK;
     }
-    for (int k = 0; k < n; k += 3) {
-        int rc = mipGenerateGroup(m, first + k, n - k < 3 ? n - k : 3, q + k, rects + k);
+    for (int k = 0; k < n;) {
+        // Large levels are bandwidth work and the lean one-launch-per-level kernels stream them best (measured: the
+        // fused kernel's region bookkeeping costs more issue slots than the saved HBM round trip is worth once a level
+        // has ~1 M texels).  Small levels are launch latency: they go through the fused kernel, up to three per launch.
+        const DevLevel& S = m->levels[first + k - 1];
+        if ((long long)S.w * S.h > g_mipFuseBelow) {
+            int rc = mipGenerateLevel(m, first + k, q[k], rects[k]);
+            if (rc) return rc;
+            k += 1;
+            continue;
+        }
+        const int g = n - k < 3 ? n - k : 3;
+        int rc = mipGenerateGroup(m, first + k, g, q + k, rects + k);
         if (rc) return rc;
+        k += g;
     }
     return B2_OK;
 }
@@ -357,8 +380,9 @@ int b2mip_generate_chain(b2mip* m, int first_quality, int cubic_from_level) {
     return b2mip_generate_levels(m, 1, n, q, b2_box2i{0, 0, m->W, m->H}, nullptr);
 }
 int b2_set_mip_fusion(int enabled) {
-    const int was = g_mipFusion ? 1 : 0;
+    const int was = g_mipFusion ? (g_mipFuseBelow >= (1ll << 40) ? 2 : 1) : 0;
     g_mipFusion = enabled != 0;
+    g_mipFuseBelow = enabled == 2 ? (1ll << 40) : (1ll << 20);
     return was;
 }
 int b2mip_sample(b2mip* m, int kind, int n, const float* level, const float* x, const float* y, float* out4) {

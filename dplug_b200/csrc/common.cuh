@@ -36,6 +36,7 @@ struct FusedArgs {
     int q[3];         // quality of the step producing level s+1+k (B2_QUALITY_*)
     int n;            // steps in this launch, 1..3
     int tile0x, tile0y, tilesX;   // first tile (in tiles of the last level) and tiles per grid row
+    unsigned long long negZero2;  // (-0.0f, -0.0f): see mip_math.cuh, mulToAdd2
 };
 
 constexpr int kMaxDiffuseLevels = 6;   // Mipmap(5): gui/dplug/gui/graphics.d:1118

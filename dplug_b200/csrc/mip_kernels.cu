@@ -11,7 +11,7 @@ namespace b2 {
 // Box kernels.  Thread = 2 destination texels (x even) when the pair is inside the rectangle: one 128-bit
 // load per source row, one 64-bit store; ragged rectangle edges fall back to single texels.
 template <bool PREMUL>
-__global__ void __launch_bounds__(256) k_box_rgba(DevLevel dst, DevLevel src, Box r) {
+__global__ void __launch_bounds__(256) k_box_rgba(DevLevel dst, DevLevel src, Box r, f32x2 nz) {
     const int xp = (r.minx >> 1) + blockIdx.x * blockDim.x + threadIdx.x;  // pair index in absolute coordinates
     const int y = r.miny + blockIdx.y * blockDim.y + threadIdx.y;
     if (y >= r.maxy) return;
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) k_box_rgba(DevLevel dst, DevLevel src, Bo
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(s0 + 2 * x));
         const uint4 b = __ldg(reinterpret_cast<const uint4*>(s1 + 2 * x));
         uint2 o;
-        if (PREMUL) o = premul4x2(a.x, a.y, b.x, b.y, a.z, a.w, b.z, b.w);
+        if (PREMUL) o = premul4x2(a.x, a.y, b.x, b.y, a.z, a.w, b.z, b.w, nz);
         else { o.x = box4(a.x, a.y, b.x, b.y); o.y = box4(a.z, a.w, b.z, b.w); }
         *reinterpret_cast<uint2*>(d + x) = o;
     } else {
@@ -306,8 +306,8 @@ void launch_box_rgba(const DevLevel& dst, const DevLevel& src, Box r, bool premu
     dim3 block(32, 8);
     int pairs = ((r.maxx + 1) >> 1) - (r.minx >> 1);
     dim3 grid = gridFor(pairs, r.maxy - r.miny, block);
-    if (premul) k_box_rgba<true><<<grid, block, 0, s>>>(dst, src, r);
-    else k_box_rgba<false><<<grid, block, 0, s>>>(dst, src, r);
+    if (premul) k_box_rgba<true><<<grid, block, 0, s>>>(dst, src, r, kNegZero2);
+    else k_box_rgba<false><<<grid, block, 0, s>>>(dst, src, r, kNegZero2);
 }
 void launch_box_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s) {
     dim3 block(32, 8);

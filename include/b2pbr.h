@@ -99,7 +99,8 @@ int b2mip_generate_chain(b2mip*, int first_quality, int cubic_from_level);
  * outside the rectangles.  out_rects (optional) receives the n updated rectangles. */
 int b2mip_generate_levels(b2mip*, int first_level, int n, const int* qualities, b2_box2i update_rect_previous_level,
                           b2_box2i* out_rects);
-/* tuning / debugging knob (process-wide): 0 = every generateLevel is its own launch; returns the previous setting */
+/* tuning / debugging knob (process-wide): 0 = every generateLevel is its own launch; 1 (default) = levels whose source
+ * has at most 2^20 texels are fused, larger ones stream level by level; 2 = fuse everything.  Returns the previous setting. */
 int b2_set_mip_fusion(int enabled);
 /* the three samplers, evaluated on the device for `n` query points (test hook for mipmap.d:149-496) */
 int b2mip_sample(b2mip*, int kind /*0 linear,1 cubic,2 linearMipmap*/, int n, const float* level, const float* x,

@@ -140,10 +140,11 @@ def test_fused_equals_level_by_level_large(b2):
         src = _rand(rng, color, w, h, sparse_alpha=True)
         a, b = b2.Mipmap(color, len(recipe), w, h), b2.Mipmap(color, len(recipe), w, h)
         a.upload(0, src); b.upload(0, src)
+        was = l.b2_set_mip_fusion(2)   # fuse every level, also the large ones
         before = a.kernelLaunches()
         ra = a.generateLevels(1, list(recipe), (0, 0, w, h))
         assert a.kernelLaunches() - before == (len(recipe) + 2) // 3
-        was = l.b2_set_mip_fusion(0)
+        l.b2_set_mip_fusion(0)
         try:
             rb = b.generateLevels(1, list(recipe), (0, 0, w, h))
             assert b.kernelLaunches() == len(recipe)

@@ -69,9 +69,23 @@ def test_exact_mip_kernels_contain_no_fused_multiply_add(b2):
         if not os.path.exists(path):
             pytest.skip("objects not kept (library built elsewhere)")
         sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
-        fused = [ln.strip() for ln in sass.splitlines() if re.search(r"\bFFMA2?\b", ln)]
-        assert not fused, (obj, fused[:3])
-        assert "FMUL2" in sass or obj != "mip_kernels.o"   # the packed pipe is actually used
+        # the only fused form allowed is mulToAdd2: FFMA2 a, b, <register holding the (-0, -0) kernel argument>.  A
+        # contracted multiply-add shows up as a scalar FFMA, or as FFMA2 whose addends are the many different
+        # registers of running sums; the legitimate ones all use the one or two registers (pairs) holding -0
+        scalar = [ln.strip() for ln in sass.splitlines() if re.search(r"\bFFMA\b", ln)]
+        assert not scalar, (obj, scalar[:3])
+        fn, per_fn = None, {}
+        for ln in sass.splitlines():
+            m = re.search(r"Function : (\S+)", ln)
+            if m:
+                fn = m.group(1)
+            elif re.search(r"\bFFMA2\b", ln):
+                add = ln.split(";")[0].split(",")[-1].strip()
+                per_fn.setdefault(fn, set()).add(re.sub(r"\.reuse|\.F32x2\.HI_LO|\.F32", "", add))
+        assert per_fn, obj
+        for fn, addends in per_fn.items():
+            assert len(addends) <= 4 and all(a.startswith("R") for a in addends), (obj, fn, sorted(addends))
+        assert "FMUL2" in sass and "FADD2" in sass                        # the packed pipe is actually used
 
 
 def test_remove_overlapping_areas_known_answer(b2):
