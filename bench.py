@@ -294,7 +294,7 @@ def run_b200(args, W, H, desc):
                    "parallelism": "independent frames per GPU, no collective" if world > 1 else "1 GPU"},
         "frame_roofline_frac": (B * args.steps / (ms * 1e-3) / 1e9) / peak,
         "roofline": {"bound": "hbm", "kernel": "k_pbr_fast (fused lighting, 8 passes)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": _traffic("k_pbr_fast@%dx%d" % (W, H)), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": B, "launch_ms": light_ms},
         "e2e": {"value": world * W * H * e2e_steps / e2e_s / 1e6, "unit": "Mpix/s",
                 "h2d_bytes_per_step": int(d.nbytes + m.nbytes + z.nbytes), "d2h_bytes_per_step": int(wfb.nbytes),
@@ -314,6 +314,15 @@ class _DevView:
 
     def __init__(self, ptr, nbytes):
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2, "strides": None}
+
+
+def _traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))[key]
+        return int(t["dram_bytes_read"] + t["dram_bytes_write"])
+    except Exception:
+        return None
 
 
 def _peak():

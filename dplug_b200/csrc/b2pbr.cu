@@ -232,7 +232,7 @@ static int mipGenerateGroup(b2mip* m, int first, int n, const int* q, const b2_b
 }
 
 // levels first .. first + n - 1, in launches of up to three levels (or level by level for row bands / fusion off)
-static int mipGenerateLevels(b2mip* m, int first, int n, const int* q, const b2_box2i* rects) {
+static int mipGenerateLevels(b2mip* m, int first, int n, const int* q, const b2_box2i* rects, bool fuseAll = false) {
     if (first < 1 || n < 0 || first + n > (int)m->levels.size()) return fail(B2_ERR_INVALID, "generateLevel: level out of range");
     if (!g_mipFusion || !mipWhole(m)) {
         for (int k = 0; k < n; ++k) {
@@ -246,7 +246,7 @@ static int mipGenerateLevels(b2mip* m, int first, int n, const int* q, const b2_
         // fused kernel's region bookkeeping costs more issue slots than the saved HBM round trip is worth once a level
         // has ~1 M texels).  Small levels are launch latency: they go through the fused kernel, up to three per launch.
         const DevLevel& S = m->levels[first + k - 1];
-        if ((long long)S.w * S.h > g_mipFuseBelow) {
+        if (!fuseAll && (long long)S.w * S.h > g_mipFuseBelow) {
             int rc = mipGenerateLevel(m, first + k, q[k], rects[k]);
             if (rc) return rc;
             k += 1;
@@ -471,6 +471,7 @@ int b2layer_create(b2layer** out, int device, int w, int h, int with_opacity) {
     }
     if (cudaMalloc((void**)&l->alloc, total) != cudaSuccess) { delete l; return fail(B2_ERR_CUDA, "b2layer_create: cudaMalloc failed"); }
     cudaMemset(l->alloc, 0, total);
+    cudaStreamSynchronize(cudaStreamLegacy);
     for (int k = 0; k < n; ++k) l->plane[k].base = l->alloc + offs[k];
     *out = l;
     return B2_OK;
@@ -494,6 +495,9 @@ int b2layer_upload(b2layer* l, int plane, const void* host, size_t pitch, const 
         CU(cudaMemcpy2D(L.base + (size_t)r.min_y * L.pitch + (size_t)r.min_x * e, (size_t)L.pitch,
                         (const uint8_t*)host + (size_t)r.min_y * pitch + (size_t)r.min_x * e, pitch, (size_t)boxW(r) * e, (size_t)boxH(r), cudaMemcpyHostToDevice));
     }
+    // a synchronous copy from pageable memory may return while the DMA from the staging buffer is still in flight;
+    // the consumers (b2pbr_draw_layer) run on non-blocking streams that the legacy stream does not order
+    CU(cudaStreamSynchronize(cudaStreamLegacy));
     return B2_OK;
 }
 }  // extern "C"
@@ -531,6 +535,8 @@ struct b2pbr {
     std::vector<cudaEvent_t> pipeEvents;
     std::vector<Box> lastBoxes;
     int lastBoxKind = -1;            // what dBoxes holds: 0 = the caller's areas, 1 = 32-column strips of them
+    int tailRow = 1 << 30, lastTailRow = 1 << 30;   // areas ending below this row are cut into 8-row strips (pipelined host call)
+    int tailRow2 = 1 << 30, lastTailRow2 = 1 << 30; // ... and below this one into 4-row strips
     int nDeviceBoxes = 0;
     int mode = B2_MODE_FAST;
     uint64_t launches = 0;
@@ -653,19 +659,40 @@ static void traceEnd(b2pbr* c) {
     cudaEventRecord(c->trace.back().end, c->stream);
 }
 
+// Rows per warp strip.  A warp walks down its strip row by row, so the strip height is the length of the kernel's
+// critical path: full-height strips (32 rows) amortise the per-strip staging best and are used whenever they already
+// fill the GPU (148 SMs x 16 resident warps); small canvases (the 620 x 330 default UI has 240 such strips) get
+// shorter strips so that the same pixels are spread over more warps.
+static int stripRowsOfArea(const b2_box2i& a, int R, int tailRow, int tailRow2) {
+    if (a.max_y > tailRow2 && R > 4) return 4;
+    return (a.max_y > tailRow && R > 8) ? 8 : R;
+}
+static int stripRowsFor(const b2_box2i* areas, int n) {
+    const int full = pbr_fast_strip_rows();
+    int R = full;
+    for (; R > 4; R >>= 1) {
+        long long strips = 0;
+        for (int k = 0; k < n; ++k) strips += (long long)((boxH(areas[k]) + R - 1) / R) * ((boxW(areas[k]) + 31) / 32);
+        if (strips >= 148 * 16) break;
+    }
+    return R;
+}
+
 // Uploads the work list of a launch.  kind 0: the caller's areas as they are (one CTA each); kind 1: the areas cut
 // into warp-sized strips of 32 columns x strip_rows rows for k_pbr_fast.  The list is kept on the device and
 // re-used while the caller passes the same areas (a full-frame tile list never changes between frames).
 static int pbrUploadBoxes(b2pbr* c, const b2_box2i* areas, int n, int kind) {
-    bool same = c->lastBoxKind == kind && (int)c->lastBoxes.size() == n && n > 0 && memcmp(c->lastBoxes.data(), areas, sizeof(Box) * n) == 0;
+    bool same = c->lastBoxKind == kind && c->lastTailRow == c->tailRow && c->lastTailRow2 == c->tailRow2 && (int)c->lastBoxes.size() == n && n > 0 &&
+                memcmp(c->lastBoxes.data(), areas, sizeof(Box) * n) == 0;
     if (same) return B2_OK;
     if (c->capturing) return fail(B2_ERR_STATE, "graph capture: composite this area list once before recording it (its work list is uploaded then)");
     std::vector<Box> work;
     if (kind == 0) work.assign((const Box*)areas, (const Box*)areas + n);
     else {
-        const int R = pbr_fast_strip_rows();
+        const int R0 = stripRowsFor(areas, n);
         for (int k = 0; k < n; ++k) {
             const b2_box2i& a = areas[k];
+            const int R = stripRowsOfArea(a, R0, c->tailRow, c->tailRow2);
             for (int y = a.min_y; y < a.max_y; y += R)
                 for (int x = a.min_x; x < a.max_x; x += 32)
                     work.push_back(Box{x, y, x + 32 < a.max_x ? x + 32 : a.max_x, y + R < a.max_y ? y + R : a.max_y});
@@ -687,6 +714,8 @@ static int pbrUploadBoxes(b2pbr* c, const b2_box2i* areas, int n, int kind) {
     }
     c->lastBoxes.assign((const Box*)areas, (const Box*)areas + n);
     c->lastBoxKind = kind;
+    c->lastTailRow = c->tailRow;
+    c->lastTailRow2 = c->tailRow2;
     c->nDeviceBoxes = m;
     return B2_OK;
 }
@@ -801,6 +830,7 @@ static int pbrCreate(b2pbr** out, int device, bool banded, int y0, int y1) {
     }
     CU(cudaMalloc((void**)&c->dExpTab, sizeof(expTab)));
     CU(cudaMemcpy(c->dExpTab, expTab, sizeof(expTab), cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(cudaStreamLegacy));   // pageable sources: see b2layer_upload
     *out = c;
     return B2_OK;
 }
@@ -1078,14 +1108,22 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
         CU(cudaStreamCreateWithFlags(&c->sIn, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&c->sOut, cudaStreamNonBlocking));
     }
-    // chunk schedule: half of what is left each time (min 64 rows), so the last chunks are small and little work
-    // remains once the final bytes have crossed PCIe, while the copy count (fixed cost each) stays low
+    // Chunk schedule.  Few chunks: with the finished rows travelling back at the same time every additional chunk
+    // costs PCIe efficiency (measured on the B200 box, tools/pcie_probe.py, 83 + 33 MB of a 4K frame: 1 chunk 1.63 ms,
+    // 4 chunks 1.72 ms, 6 chunks 1.79 ms).  A small last chunk: whatever is composited after the final bytes have
+    // arrived is the exposed tail of the call.  The diffuse map runs `ahead` rows in front of the other two, because
+    // it is the bloom (94 rows of diffuse below a tile) that makes tiles wait; depth needs 28 rows.
+    const int ahead = 128;
     std::vector<int> bounds{0};
-    while (bounds.back() < H) {
-        int left = H - bounds.back();
-        int ch = ((left + 1) / 2 + 63) / 64 * 64;
-        if (ch < 64) ch = 64;
-        bounds.push_back(bounds.back() + (ch < left ? ch : left));
+    {
+        // Sizes from a fluid model of the measured rates (uploads 1.27 rows/us, kernels 5.3 rows/us plus ~100 us of
+        // dependent launches per stage): a stage must finish before the next chunk has arrived,
+        // s[k+1] >= 127 + 0.24 s[k], and the last chunk — whose stage and copy-back are exposed — is as small as that allows.
+        auto r64 = [](double v) { return (int)((v + 32.0) / 64.0) * 64; };
+        const int cuts[3] = {r64(0.44 * H), r64(0.77 * H), r64(0.91 * H)};
+        for (int cut : cuts)
+            if (cut >= bounds.back() + 128 && cut < H) bounds.push_back(cut);
+        bounds.push_back(H);
     }
     const int nChunks = (int)bounds.size() - 1;
     while ((int)c->pipeEvents.size() < 2 * nChunks + 1) {
@@ -1095,7 +1133,9 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
     }
     static const bool dbg = getenv("B2_PIPE_DEBUG") != nullptr;
     cudaEvent_t d0 = nullptr, d1 = nullptr, d2 = nullptr, d3 = nullptr;
+    std::vector<cudaEvent_t> dIn, dK0, dK1, dK2;   // per chunk: upload done, stage start, mips done, tiles done
     if (dbg) { cudaEventCreate(&d0); cudaEventCreate(&d1); cudaEventCreate(&d2); cudaEventCreate(&d3); }
+    auto mark = [&](std::vector<cudaEvent_t>& v, cudaStream_t st) { if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); v.push_back(e); } };
     // uploads must not overtake kernels of a previous call that still read the maps
     CU(cudaEventRecord(c->pipeEvents[2 * nChunks], c->stream));
     CU(cudaStreamWaitEvent(c->sIn, c->pipeEvents[2 * nChunks], 0));
@@ -1107,59 +1147,100 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return areas[a].max_y < areas[b].max_y; });
     std::vector<b2_box2i> sorted(n_areas);
     for (int k = 0; k < n_areas; ++k) sorted[k] = areas[order[k]];
-    const int R = pbr_fast_strip_rows();
+    // the tiles composited after the last bytes have arrived are the exposed tail of the call: short strips spread them
+    // over the whole GPU (results do not depend on the strip cut)
+    auto diffuseUpTo = [&](int k) { int v = bounds[k] + (k > 0 ? ahead : 0); return (k == nChunks || v > H) ? H : v; };   // rows of diffuse present after chunk k-1
+    struct TailGuard { b2pbr* c; ~TailGuard() { c->tailRow = c->tailRow2 = 1 << 30; } } tailGuard{c};
+    // rows [0, cEnd[k]) can be composited once chunk k has arrived: every level-0 row their passes (and the mip rows
+    // they sample) read is present — diffuse up to diffuseUpTo(k + 1), depth and material up to bounds[k + 1]
+    std::vector<int> cEnd(nChunks, 0);
+    {
+        int nd[kMaxDiffuseLevels][2], nz[kMaxDepthLevels][2], prev = 0;
+        for (int k = 0; k < nChunks; ++k) {
+            const int y1 = bounds[k + 1], yD = diffuseUpTo(k + 1);
+            int cNew = prev;
+            if (y1 == H) cNew = H;
+            else
+                for (int t = prev + 64; t <= y1; t += 64) {
+                    computeBandNeeds(W, H, prev, t, nd, nz);
+                    if (nd[0][1] > yD || nz[0][1] > y1) break;
+                    cNew = t;
+                }
+            cEnd[k] = prev = cNew;
+        }
+    }
+    // the last two stages run next to (and after) the end of the transfer: shorter strips, every mip level fused
+    c->tailRow = nChunks >= 3 ? cEnd[nChunks - 3] : H - 256;
+    c->tailRow2 = nChunks >= 2 ? cEnd[nChunks - 2] : H - 128;
+    const int R0 = stripRowsFor(areas, n_areas);
     auto workItems = [&](const b2_box2i& a, bool fast) {
         if (!fast) return 1;
+        const int R = stripRowsOfArea(a, R0, c->tailRow, c->tailRow2);
         return ((boxH(a) + R - 1) / R) * ((boxW(a) + 31) / 32);
     };
+    // stage 1: every upload is enqueued up front, so the copy engine never waits for this thread (the host-side cost
+    // of enqueueing a stage's kernels is comparable to the transfer time of the small last chunks)
+    for (int k = 0; k < nChunks; ++k) {
+        struct { b2mip* m; b2_imageref im; int y0, y1; } ups[3] = {{c->diffuse, dI, diffuseUpTo(k), diffuseUpTo(k + 1)},
+                                                                     {c->material, mI, bounds[k], bounds[k + 1]},
+                                                                     {c->depth, zI, bounds[k], bounds[k + 1]}};
+        for (auto& u : ups) {
+            if (u.y1 <= u.y0) continue;
+            const DevLevel& L = u.m->levels[0];
+            uint8_t* dst = L.base + (size_t)(u.y0 - L.y0) * L.pitch;
+            const uint8_t* src = (const uint8_t*)u.im.pixels + (size_t)u.y0 * u.im.pitch;
+            if ((size_t)L.pitch == u.im.pitch && (size_t)W * u.m->elem == u.im.pitch)   // gapless on both sides: one linear copy
+                CU(cudaMemcpyAsync(dst, src, u.im.pitch * (size_t)(u.y1 - u.y0), cudaMemcpyHostToDevice, c->sIn));
+            else
+                CU(cudaMemcpy2DAsync(dst, (size_t)L.pitch, src, u.im.pitch, (size_t)W * u.m->elem, (size_t)(u.y1 - u.y0), cudaMemcpyHostToDevice, c->sIn));
+        }
+        CU(cudaEventRecord(c->pipeEvents[2 * k], c->sIn));
+        mark(dIn, c->sIn);
+    }
+    if (dbg) cudaEventRecord(d1, c->sIn);
     size_t pos = 0;
     int workPos = 0;
     int cPrev = 0;
     int genD[kMaxDiffuseLevels] = {0}, genZ[kMaxDepthLevels] = {0};
     const int nD = (int)c->diffuse->levels.size(), nZ = (int)c->depth->levels.size();
     std::vector<b2_box2i> merged;
+    const uint64_t mipLaunches0 = c->diffuse->launches + c->depth->launches;
     for (int k = 0; k < nChunks; ++k) {
-        const int y0 = bounds[k], y1 = bounds[k + 1];
-        struct { b2mip* m; b2_imageref im; } ups[3] = {{c->diffuse, dI}, {c->material, mI}, {c->depth, zI}};
-        for (auto& u : ups) {
-            const DevLevel& L = u.m->levels[0];
-            uint8_t* dst = L.base + (size_t)(y0 - L.y0) * L.pitch;
-            const uint8_t* src = (const uint8_t*)u.im.pixels + (size_t)y0 * u.im.pitch;
-            if ((size_t)L.pitch == u.im.pitch && (size_t)W * u.m->elem == u.im.pitch)   // gapless on both sides: one linear copy
-                CU(cudaMemcpyAsync(dst, src, u.im.pitch * (size_t)(y1 - y0), cudaMemcpyHostToDevice, c->sIn));
-            else
-                CU(cudaMemcpy2DAsync(dst, (size_t)L.pitch, src, u.im.pitch, (size_t)W * u.m->elem, (size_t)(y1 - y0), cudaMemcpyHostToDevice, c->sIn));
-        }
-        CU(cudaEventRecord(c->pipeEvents[2 * k], c->sIn));
         CU(cudaStreamWaitEvent(c->stream, c->pipeEvents[2 * k], 0));
-        // rows that can be composited now: every level-0 row their passes (and the mip rows they sample) read is < y1
-        int cNew = cPrev;
+        const int cNew = cEnd[k];
         int nd[kMaxDiffuseLevels][2], nz[kMaxDepthLevels][2];
-        if (y1 == H) cNew = H;
-        else
-            for (int t = cPrev + 64; t <= H; t += 64) {
-                computeBandNeeds(W, H, cPrev, t, nd, nz);
-                if (nd[0][1] > y1 || nz[0][1] > y1) break;
-                cNew = t;
-            }
         if (cNew == cPrev) continue;
         computeBandNeeds(W, H, cPrev, cNew, nd, nz);
-        for (int l = 1; l < nD; ++l) {
-            if (nd[l][1] <= genD[l]) continue;
-            int q = l == 1 ? B2_QUALITY_BOX_ALPHACOV_PREMUL : B2_QUALITY_CUBIC;   // graphics.d:1380-1384
-            int rc = mipGenerateLevel(c->diffuse, l, q, b2_box2i{0, genD[l], c->diffuse->levels[l].w, nd[l][1]});
+        mark(dK0, c->stream);
+        {   // the mip rows that became computable, as one chain per pyramid (small levels share launches)
+            int q[kMaxDiffuseLevels];
+            b2_box2i rects[kMaxDiffuseLevels];
+            for (int l = 1; l < nD; ++l) {
+                q[l - 1] = l == 1 ? B2_QUALITY_BOX_ALPHACOV_PREMUL : B2_QUALITY_CUBIC;   // graphics.d:1380-1384
+                const int hi = nd[l][1] > genD[l] ? nd[l][1] : genD[l];
+                rects[l - 1] = b2_box2i{0, genD[l], c->diffuse->levels[l].w, hi};
+                genD[l] = hi;
+            }
+            // the two pyramids are independent: the depth chain runs beside the diffuse chain (as in regenerateMipmaps)
+            CU(cudaEventRecord(c->evFork, c->stream));
+            CU(cudaStreamWaitEvent(c->sAux, c->evFork, 0));
+            const bool late = k >= nChunks - 2;
+            int rc = mipGenerateLevels(c->diffuse, 1, nD - 1, q, rects, late);
             if (rc) return rc;
-            genD[l] = nd[l][1];
-            c->launches++;
-        }
-        for (int l = 1; l < nZ; ++l) {
-            if (nz[l][1] <= genZ[l]) continue;
-            int q = l >= 3 ? B2_QUALITY_CUBIC : B2_QUALITY_BOX;                    // graphics.d:1414
-            int rc = mipGenerateLevel(c->depth, l, q, b2_box2i{0, genZ[l], c->depth->levels[l].w, nz[l][1]});
+            for (int l = 1; l < nZ; ++l) {
+                q[l - 1] = l >= 3 ? B2_QUALITY_CUBIC : B2_QUALITY_BOX;                    // graphics.d:1414
+                const int hi = nz[l][1] > genZ[l] ? nz[l][1] : genZ[l];
+                rects[l - 1] = b2_box2i{0, genZ[l], c->depth->levels[l].w, hi};
+                genZ[l] = hi;
+            }
+            c->depth->stream = c->sAux;
+            rc = mipGenerateLevels(c->depth, 1, nZ - 1, q, rects, late);
+            c->depth->stream = c->stream;
             if (rc) return rc;
-            genZ[l] = nz[l][1];
-            c->launches++;
+            CU(cudaEventRecord(c->evJoin, c->sAux));
+            CU(cudaStreamWaitEvent(c->stream, c->evJoin, 0));
         }
+        mark(dK1, c->stream);
         const size_t first = pos;
         while (pos < sorted.size() && sorted[pos].max_y <= cNew) ++pos;
         if (pos > first) {
@@ -1172,23 +1253,35 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
             rc = pbrComposite(c, sorted.data(), n_areas, nullptr, nullptr, nullptr, workPos, cnt, nullptr);
             if (rc) return rc;
             workPos += cnt;
+            mark(dK2, c->stream);
             CU(cudaEventRecord(c->pipeEvents[2 * k + 1], c->stream));
             CU(cudaStreamWaitEvent(c->sOut, c->pipeEvents[2 * k + 1], 0));
             mergeRects(sorted.data() + first, (int)(pos - first), merged);
-            for (const b2_box2i& r : merged)
-                CU(cudaMemcpy2DAsync((uint8_t*)wfb.pixels + (size_t)r.min_y * wfb.pitch + (size_t)r.min_x * 4, wfb.pitch,
-                                     c->out.base + (size_t)(r.min_y - c->out.y0) * c->out.pitch + (size_t)r.min_x * 4, (size_t)c->out.pitch,
-                                     (size_t)boxW(r) * 4, (size_t)boxH(r), cudaMemcpyDeviceToHost, c->sOut));
+            for (const b2_box2i& r : merged) {
+                uint8_t* hp = (uint8_t*)wfb.pixels + (size_t)r.min_y * wfb.pitch + (size_t)r.min_x * 4;
+                const uint8_t* dp = c->out.base + (size_t)(r.min_y - c->out.y0) * c->out.pitch + (size_t)r.min_x * 4;
+                if (r.min_x == 0 && r.max_x == W && wfb.pitch == (size_t)c->out.pitch && wfb.pitch == (size_t)W * 4)   // whole rows, gapless
+                    CU(cudaMemcpyAsync(hp, dp, wfb.pitch * (size_t)boxH(r), cudaMemcpyDeviceToHost, c->sOut));
+                else
+                    CU(cudaMemcpy2DAsync(hp, wfb.pitch, dp, (size_t)c->out.pitch, (size_t)boxW(r) * 4, (size_t)boxH(r), cudaMemcpyDeviceToHost, c->sOut));
+            }
         }
         cPrev = cNew;
     }
-    if (dbg) { cudaEventRecord(d1, c->sIn); cudaEventRecord(d2, c->stream); cudaEventRecord(d3, c->sOut); }
+    c->launches += c->diffuse->launches + c->depth->launches - mipLaunches0;
+    if (dbg) { cudaEventRecord(d2, c->stream); cudaEventRecord(d3, c->sOut); }
     CU(cudaStreamSynchronize(c->sOut));
     CU(cudaStreamSynchronize(c->stream));
     if (dbg) {
         float a = 0, b = 0, e = 0;
         cudaEventElapsedTime(&a, d0, d1); cudaEventElapsedTime(&b, d0, d2); cudaEventElapsedTime(&e, d0, d3);
         fprintf(stderr, "[b2pbr pipe] chunks=%d  H2D done %.3f ms, kernels done %.3f ms, D2H done %.3f ms\n", nChunks, a, b, e);
+        auto dump = [&](const char* name, std::vector<cudaEvent_t>& v) {
+            fprintf(stderr, "[b2pbr pipe]   %s:", name);
+            for (cudaEvent_t ev : v) { float t = 0; cudaEventElapsedTime(&t, d0, ev); fprintf(stderr, " %.3f", t); cudaEventDestroy(ev); }
+            fprintf(stderr, "\n");
+        };
+        dump("upload done", dIn); dump("stage start", dK0); dump("mips done", dK1); dump("tiles done", dK2);
         cudaEventDestroy(d0); cudaEventDestroy(d1); cudaEventDestroy(d2); cudaEventDestroy(d3);
     }
     return B2_OK;
