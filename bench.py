@@ -23,6 +23,7 @@ WORKLOADS = {
     "c1": (620, 330, "C1 examples/distort default size 620x330, full-frame composite"),
     "c2": (3840, 2160, "C2 synthetic 3840x2160 diffuse/material/depth, full re-composite"),
     "c3": (8192, 8192, "C3 emissive Mipmap bloom pyramid (generateNextLevel, 8 levels) on 8192x8192 RGBA"),
+    "c4": (2048, 1024, "C4 batch of 256 plug-in-instance UIs at 2048x1024, instances dealt out over the GPUs (one step = the whole batch)"),
     "c5": (16384, 16384, "C5 16384x16384 single canvas row-banded over the GPUs, level-0 halo exchange per frame"),
 }
 
@@ -174,13 +175,22 @@ def run_b200(args, W, H, desc):
 
     # R independent plug-in UIs per GPU, visited round-robin, so every step works on inputs that the previous
     # steps evicted from the 126 MB L2 (R * ~133 MB of maps)
-    R = args.instances
+    batch = args.workload == "c4"   # one step = every instance of the batch once (strong scaling: 256 UIs in total)
+    if batch:
+        from dplug_b200 import sharding
+        R = len(sharding.instances_for_rank(256, rank, world))
+    else:
+        R = args.instances
     tiles = b2.BoxArray(b2.tileAreas([(0, 0, W, H)], 64, 64))   # marshalled once, like the D slice the caller keeps
     whole = b2.BoxArray([(0, 0, W, H)])
     sky = synth.skybox()
     comps, hosts = [], []
+    distinct = {}
     for k in range(R):
-        d, m, z = synth.frame(W, H, synth.SEED + 1000 * rank + k)
+        seed = synth.SEED + 1000 * rank + (k % 8 if batch else k)   # the batch re-uses 8 distinct synthetic UIs per rank
+        if seed not in distinct:
+            distinct[seed] = synth.frame(W, H, seed)
+        d, m, z = distinct[seed]
         c = b2.PBRCompositor(local)
         c.resizeBuffers(W, H, 64, 64)
         c.set_stream(stream.cuda_stream)
@@ -194,6 +204,13 @@ def run_b200(args, W, H, desc):
     graphs = {}
 
     def step(i):
+        if batch:
+            for k in range(R):
+                one(k)
+        else:
+            one(i % R)
+
+    def one(i):
         c = comps[i % R]
         if args.graph and (i % R) in graphs:
             c.graphLaunch(graphs[i % R])     # the same two calls, replayed from a CUDA graph
@@ -207,7 +224,7 @@ def run_b200(args, W, H, desc):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(max(3, args.warmup, R)):
+    for i in range(max(3, args.warmup) if batch else max(3, args.warmup, R)):
         step(i)
     barrier()
     if args.graph:
@@ -216,7 +233,7 @@ def run_b200(args, W, H, desc):
             c.regenerateMipmaps(whole)
             c.compositeTile(None, tiles)
             graphs[k] = c.graphEnd()
-        for i in range(R):
+        for i in range(1 if batch else R):
             step(i)
         barrier()
     launches0 = sum(c.kernelLaunches() for c in comps)
@@ -242,7 +259,7 @@ def run_b200(args, W, H, desc):
     # frame sequence (the mip regeneration of the same frame runs before it, untimed, so the cache state is the
     # timed region's)
     evs = []
-    for i in range(args.steps):
+    for i in range(min(args.steps, 200)):
         c = comps[i % R]
         c.regenerateMipmaps(whole)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -258,12 +275,15 @@ def run_b200(args, W, H, desc):
     c = comps[0]
     d, m, z = hosts
     for _ in range(2):
-        c.compositeTile(wfb, tiles, d, m, z, updateRects=whole)
+        for k in range(R if batch else 1):
+            comps[k].compositeTile(wfb, tiles, d, m, z, updateRects=whole)
     barrier()
     e2e_steps = max(3, min(args.steps, 10))
+    per_step = R if batch else 1      # the batch: every instance of this rank goes through the host-image call
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        c.compositeTile(wfb, tiles, d, m, z, updateRects=whole)   # synchronises on the copy-back
+        for k in range(per_step):
+            comps[k].compositeTile(wfb, tiles, d, m, z, updateRects=whole)   # synchronises on the copy-back
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -284,20 +304,22 @@ def run_b200(args, W, H, desc):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     B = algorithmic_bytes_frame(W, H)
     achieved = B / (light_ms * 1e-3) / 1e9 if light_ms > 0 else 0.0
-    value = world * W * H * args.steps / (ms * 1e-3) / 1e6
+    frames_per_step = 256 if batch else world   # whole job, all ranks
+    value = frames_per_step * W * H * args.steps / (ms * 1e-3) / 1e6
     out = {
         "metric": "composited Mpix/s (full PBR frame)", "value": value, "unit": "Mpix/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong" if batch else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (8 distinct UIs per GPU, re-used across the batch)" if batch else "synthetic",
         "config": {"workload": desc, "tile": "64x64", "instances_per_gpu": R, "cuda_graph": bool(args.graph),
                    "l2": "inputs larger than L2: %d independent frames (%.0f MB) visited round-robin" % (R, R * B / 1e6),
                    "parallelism": "independent frames per GPU, no collective" if world > 1 else "1 GPU"},
-        "frame_roofline_frac": (B * args.steps / (ms * 1e-3) / 1e9) / peak,
+        "frame_roofline_frac": (B * (R if batch else 1) * args.steps / (ms * 1e-3) / 1e9) / peak,
         "roofline": {"bound": "hbm", "kernel": "k_pbr_fast (fused lighting, 8 passes)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": _traffic("k_pbr_fast@%dx%d" % (W, H)), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": B, "launch_ms": light_ms},
-        "e2e": {"value": world * W * H * e2e_steps / e2e_s / 1e6, "unit": "Mpix/s",
-                "h2d_bytes_per_step": int(d.nbytes + m.nbytes + z.nbytes), "d2h_bytes_per_step": int(wfb.nbytes),
+        "e2e": {"value": frames_per_step * W * H * e2e_steps / e2e_s / 1e6, "unit": "Mpix/s",
+                "h2d_bytes_per_step": int(d.nbytes + m.nbytes + z.nbytes) * per_step, "d2h_bytes_per_step": int(wfb.nbytes) * per_step,
                 "call": "b2pbr_composite_tile_host (ICompositor.compositeTile with host images, pinned)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
