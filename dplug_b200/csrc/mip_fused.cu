@@ -197,13 +197,27 @@ __device__ __forceinline__ void stageRegion(const DevLevel& src, Iv rx, Iv ry, c
     const int x0 = out.x0 & ~(E - 1);  // (for L16, x0 is only even: fall back to 32-bit words there)
     if (sizeof(T) == 4 || x0 == out.x0) {
         const int nw = (rx.b - x0 + E - 1) / E;
-        for (int y = ry.a + warp; y < ry.b; y += FUSED_THREADS / 32) {
-            const T* srow = rowPtr<T>(src, y);
-            T* drow = &out.at(x0, y);
+        // UR rows per warp and pass, loads first: a small-level launch is a chain of short phases, and a row-by-row
+        // copy would expose one L2 round trip per row
+        constexpr int UR = 4, WARPS = FUSED_THREADS / 32;
+        for (int yb = ry.a + warp; yb < ry.b; yb += WARPS * UR) {
             for (int wI = lane; wI < nw; wI += 32) {
                 const int x = x0 + wI * E;
-                if (x + E <= src.w) *reinterpret_cast<uint2*>(drow + wI * E) = __ldg(reinterpret_cast<const uint2*>(srow + x));
-                else for (int t = 0; x + t < src.w && t < E; ++t) drow[wI * E + t] = __ldg(srow + x + t);
+                const bool whole = x + E <= src.w;
+                uint2 v[UR];
+#pragma unroll
+                for (int k = 0; k < UR; ++k) {
+                    const int y = yb + k * WARPS;
+                    if (y < ry.b && whole) v[k] = __ldg(reinterpret_cast<const uint2*>(rowPtr<T>(src, y) + x));
+                }
+#pragma unroll
+                for (int k = 0; k < UR; ++k) {
+                    const int y = yb + k * WARPS;
+                    if (y >= ry.b) continue;
+                    T* drow = &out.at(x0, y);
+                    if (whole) *reinterpret_cast<uint2*>(drow + wI * E) = v[k];
+                    else for (int t = 0; x + t < src.w && t < E; ++t) drow[wI * E + t] = __ldg(rowPtr<T>(src, y) + x + t);
+                }
             }
         }
     } else {
