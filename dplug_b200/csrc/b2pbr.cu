@@ -1109,7 +1109,7 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
         CU(cudaStreamCreateWithFlags(&c->sOut, cudaStreamNonBlocking));
     }
     // Chunk schedule.  Few chunks: with the finished rows travelling back at the same time every additional chunk
-    // costs PCIe efficiency (measured on the B200 box, tools/pcie_probe.py, 83 + 33 MB of a 4K frame: 1 chunk 1.63 ms,
+    // costs PCIe efficiency (measured on the B200 box, tools/probes/pcie_probe.py, 83 + 33 MB of a 4K frame: 1 chunk 1.63 ms,
     // 4 chunks 1.72 ms, 6 chunks 1.79 ms).  A small last chunk: whatever is composited after the final bytes have
     // arrived is the exposed tail of the call.  The diffuse map runs `ahead` rows in front of the other two, because
     // it is the bloom (94 rows of diffuse below a tile) that makes tiles wait; depth needs 28 rows.

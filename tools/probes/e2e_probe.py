@@ -1,6 +1,6 @@
 """Times the host-image call (b2pbr_composite_tile_host) and its parts on the GPU box (profiling aid)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import dplug_b200 as b2
 from dplug_b200 import synth
