@@ -1,9 +1,12 @@
+// Probe for the ptxas FMUL2+FADD2 -> FFMA2 contraction (dplug_b200/csrc/mip_math.cuh): evaluates one 2x2 quad with the
+// packed premultiplying box, the scalar one and step-by-step intrinsics, and prints the intermediate values.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -o premul_rounding_probe premul_rounding_probe.cu
 #include <cstdio>
 #include "../../dplug_b200/csrc/mip_math.cuh"
 using namespace b2;
-__global__ void k(const uint32_t* q, uint32_t* out, float* f) {
+__global__ void k(const uint32_t* q, uint32_t* out, float* f, f32x2 nz) {
     // quad 0 = q[0..3], quad 1 = q[4..7]
-    uint2 o = premul4x2(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7]);
+    uint2 o = premul4x2(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], nz);
     out[0] = o.x; out[1] = o.y;
     out[2] = premul4(q[0], q[1], q[2], q[3]);
     out[3] = premul4(q[4], q[5], q[6], q[7]);
@@ -31,7 +34,7 @@ __global__ void k(const uint32_t* q, uint32_t* out, float* f) {
         out[4 + quad] = r;
     }
     // packed intermediates for quad pair
-    Lin4x2 A = premulLinear2(q[0], q[4]), B = premulLinear2(q[1], q[5]), C = premulLinear2(q[2], q[6]), D = premulLinear2(q[3], q[7]);
+    Lin4x2 A = premulLinear2(q[0], q[4], nz), B = premulLinear2(q[1], q[5], nz), C = premulLinear2(q[2], q[6], nz), D = premulLinear2(q[3], q[7], nz);
     float lo, hi;
     unpack2(A.g, lo, hi); f[64] = lo; unpack2(B.g, lo, hi); f[65] = lo; unpack2(C.g, lo, hi); f[66] = lo; unpack2(D.g, lo, hi); f[67] = lo;
     f32x2 g = add2(add2(add2(A.g, B.g), C.g), D.g);
@@ -48,7 +51,7 @@ int main() {
     uint32_t *dq, *dout; float* df;
     cudaMalloc(&dq, 32); cudaMalloc(&dout, 32); cudaMalloc(&df, 4 * 128);
     cudaMemcpy(dq, hq, 32, cudaMemcpyHostToDevice);
-    k<<<1, 1>>>(dq, dout, df);
+    k<<<1, 1>>>(dq, dout, df, kNegZero2);
     uint32_t ho[8]; float hf[128];
     cudaMemcpy(ho, dout, 32, cudaMemcpyDeviceToHost); cudaMemcpy(hf, df, 512, cudaMemcpyDeviceToHost);
     printf("x2: %08x %08x  old: %08x %08x  scalar: %08x %08x  (%s)\n", ho[0], ho[1], ho[2], ho[3], ho[4], ho[5], cudaGetErrorString(cudaGetLastError()));
