@@ -55,6 +55,12 @@ SIGNATURES = {
     "b2mip_generate_chain": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "b2mip_generate_levels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), box2i, C.POINTER(box2i)]),
     "b2_set_mip_fusion": (C.c_int, [C.c_int]),
+    "b2_dirty_rects_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "b2_dirty_rects_destroy": (None, [C.c_void_p]),
+    "b2_dirty_rects_add": (C.c_int, [C.c_void_p, box2i]),
+    "b2_dirty_rects_is_empty": (C.c_int, [C.c_void_p]),
+    "b2_dirty_rects_pull_all": (C.c_int, [C.c_void_p, C.POINTER(box2i), C.c_int]),
+    "b2_have_no_overlap": (C.c_int, [C.POINTER(box2i), C.c_int]),
     "b2mip_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2mip_sync": (C.c_int, [C.c_void_p]),
     "b2mip_kernel_launches": (C.c_uint64, [C.c_void_p]),

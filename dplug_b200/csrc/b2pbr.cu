@@ -431,6 +431,31 @@ int b2_remove_overlapping_areas(b2_box2i* boxes, int n, b2_box2i* out, int cap) 
 }
 b2_box2i b2_grow_rect(b2_box2i rect, int margin, int width, int height) { return growRect(rect, margin, width, height); }
 
+struct b2_dirty_rects { DirtyRectList list; std::vector<b2_box2i> pulled; };
+int b2_dirty_rects_create(b2_dirty_rects** out) {
+    if (!out) return fail(B2_ERR_INVALID, "dirty_rects_create: null");
+    *out = new b2_dirty_rects();
+    return B2_OK;
+}
+void b2_dirty_rects_destroy(b2_dirty_rects* d) { delete d; }
+int b2_dirty_rects_add(b2_dirty_rects* d, b2_box2i rect) {
+    if (!d || !boxSorted(rect)) return fail(B2_ERR_INVALID, "addRect: the rectangle must be sorted (boxlist.d:239)");
+    d->list.addRect(rect);
+    return B2_OK;
+}
+int b2_dirty_rects_is_empty(b2_dirty_rects* d) { return (!d || (d->pulled.empty() && d->list.isEmpty())) ? 1 : 0; }
+int b2_dirty_rects_pull_all(b2_dirty_rects* d, b2_box2i* out, int cap) {
+    if (!d || cap < 0 || (cap > 0 && !out)) return 0;
+    d->list.pullAllRectangles(d->pulled);      // rectangles a too-small buffer could not take stay queued here
+    const int n = (int)d->pulled.size();
+    if (n <= cap) {
+        for (int i = 0; i < n; ++i) out[i] = d->pulled[i];
+        d->pulled.clear();
+    }
+    return n;
+}
+int b2_have_no_overlap(const b2_box2i* boxes, int n) { return (n <= 0 || (boxes && haveNoOverlap(boxes, n))) ? 1 : 0; }
+
 int b2_host_register(void* ptr, size_t bytes) {
     CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
     return B2_OK;

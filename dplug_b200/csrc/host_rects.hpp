@@ -3,6 +3,7 @@
 // tileAreas / removeOverlappingAreas (gui/dplug/gui/boxlist.d:54-167) and
 // convertPBRLayerRectToRawLayerRect (gui/dplug/gui/graphics.d:981-1002).
 #pragma once
+#include <mutex>
 #include <vector>
 #include "../../include/b2pbr.h"
 
@@ -78,6 +79,61 @@ inline void removeOverlappingAreas(std::vector<b2_box2i>& boxes, std::vector<b2_
         if (!split) filtered.push_back(A);
     }
 }
+
+// box.d:321-325 — two boxes intersect when their (sorted) intersection is not empty
+inline bool boxIntersects(const b2_box2i& a, const b2_box2i& b) {
+    const b2_box2i c = boxIntersect(a, b);
+    return boxSorted(c) && !boxEmpty(c);
+}
+inline bool haveNoOverlap(const b2_box2i* areas, int n) {   // boxlist.d:171-186
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j)
+            if (boxIntersects(areas[i], areas[j])) return false;
+    return true;
+}
+
+// The widgets' dirty-rectangle accumulator (DirtyRectList, gui/dplug/gui/boxlist.d:200-303): rectangles are added
+// from the UI thread and from host parameter-change callbacks (hence the lock), the draw thread pulls the whole
+// list.  The list never holds overlapping rectangles: a new rectangle that lies inside an element is dropped,
+// elements inside it are removed, and elements it cuts are replaced by their up-to-four remainders.
+class DirtyRectList {
+public:
+    bool isEmpty() {
+        std::lock_guard<std::mutex> g(lock_);
+        return rects_.empty();
+    }
+    void pullAllRectangles(std::vector<b2_box2i>& out) {   // appends, then clears (boxlist.d:224-234)
+        std::lock_guard<std::mutex> g(lock_);
+        out.insert(out.end(), rects_.begin(), rects_.end());
+        rects_.clear();
+    }
+    void addRect(const b2_box2i& rect) {
+        if (boxEmpty(rect)) return;
+        std::lock_guard<std::mutex> g(lock_);
+        size_t i = 0;
+        while (i < rects_.size()) {
+            const b2_box2i other = rects_[i];
+            if (boxContains(other, rect)) return;            // already covered
+            const bool swallowed = boxContains(rect, other);
+            const b2_box2i common = swallowed ? other : boxIntersect(other, rect);
+            if (!swallowed && boxEmpty(common)) { ++i; continue; }   // disjoint: keep
+            // `other` leaves the list (the last element takes its slot and is examined next) ...
+            rects_[i] = rects_.back();
+            rects_.pop_back();
+            if (swallowed) continue;
+            // ... and what is left of it outside the new rectangle goes to the end: above, left, right, below
+            const b2_box2i rest[4] = {{other.min_x, other.min_y, other.max_x, common.min_y}, {other.min_x, common.min_y, common.min_x, common.max_y},
+                                      {common.max_x, common.min_y, other.max_x, common.max_y}, {other.min_x, common.max_y, other.max_x, other.max_y}};
+            for (const b2_box2i& r : rest)
+                if (!boxEmpty(r)) rects_.push_back(r);
+        }
+        rects_.push_back(rect);
+    }
+
+private:
+    std::vector<b2_box2i> rects_;
+    std::mutex lock_;
+};
 
 // Coalesces a list of disjoint rectangles for bulk copies: horizontally adjacent boxes with the same rows are
 // joined, then vertically adjacent spans with the same columns (a full-frame 64x64 tile list collapses to one

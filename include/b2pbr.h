@@ -107,6 +107,17 @@ int b2mip_sample(b2mip*, int kind /*0 linear,1 cubic,2 linearMipmap*/, int n, co
                  const float* y, float* out4);
 int b2mip_sync(b2mip*);
 
+/* ---- dirty-rectangle accumulator — DirtyRectList, gui/dplug/gui/boxlist.d:200-303 (host-side, thread-safe like the
+ * reference's: addRect may be called from any thread, the draw thread pulls).  haveNoOverlap: boxlist.d:171-186. */
+typedef struct b2_dirty_rects b2_dirty_rects;
+int b2_dirty_rects_create(b2_dirty_rects** out);                                   /* makeDirtyRectList */
+void b2_dirty_rects_destroy(b2_dirty_rects*);
+int b2_dirty_rects_add(b2_dirty_rects*, b2_box2i rect);                            /* addRect (rect must be sorted) */
+int b2_dirty_rects_is_empty(b2_dirty_rects*);                                      /* isEmpty */
+int b2_dirty_rects_pull_all(b2_dirty_rects*, b2_box2i* out, int cap);              /* pullAllRectangles: returns the count;
+                                                                                    * the list is emptied only if cap suffices */
+int b2_have_no_overlap(const b2_box2i* boxes, int n);
+
 /* rectangle propagation — Mipmap.impactOnNextLevel, mipmap.d:623-645 (host-side, no device work) */
 b2_box2i b2_impact_on_next_level(int quality, b2_box2i area, int current_level_w, int current_level_h);
 /* tileAreas — gui/dplug/gui/boxlist.d:139-167; returns the number of tiles (writes at most `cap`) */

@@ -177,6 +177,12 @@ b2ref_box2i b2ref_bounding_box(const b2ref_box2i* boxes, int n) {
     std::vector<box2i> in((const box2i*)boxes, (const box2i*)boxes + n);
     return fromBox(boundingBox(in));
 }
+int b2ref_dirty_rect_list_add(b2ref_box2i* list, int n, int cap, b2ref_box2i rect) {
+    std::vector<box2i> v((const box2i*)list, (const box2i*)list + n);
+    dirtyRectListAdd(v, toBox(rect));
+    for (int i = 0; i < (int)v.size() && i < cap; ++i) list[i] = fromBox(v[i]);
+    return (int)v.size();
+}
 int b2ref_have_no_overlap(const b2ref_box2i* boxes, int n) { return haveNoOverlap((const box2i*)boxes, n) ? 1 : 0; }
 b2ref_box2i b2ref_impact_on_next_level(int quality, b2ref_box2i area, int w, int h) {
     return fromBox(Mipmap<RGBA>::impactOnNextLevel(quality, toBox(area), w, h));

@@ -77,6 +77,8 @@ int b2ref_tile_areas(const b2ref_box2i* areas, int n, int max_w, int max_h, b2re
 int b2ref_remove_overlapping_areas(b2ref_box2i* boxes, int n, b2ref_box2i* out, int cap);
 b2ref_box2i b2ref_bounding_box(const b2ref_box2i* boxes, int n);
 int b2ref_have_no_overlap(const b2ref_box2i* boxes, int n);
+/* DirtyRectList.addRect (boxlist.d:236-292) on a caller-held list of *n rectangles (capacity cap); returns the new count */
+int b2ref_dirty_rect_list_add(b2ref_box2i* list, int n, int cap, b2ref_box2i rect);
 b2ref_box2i b2ref_impact_on_next_level(int quality, b2ref_box2i area, int w, int h);
 
 /* ---- scalar helpers, exposed for unit tests */

@@ -278,6 +278,9 @@ inline float pow_ps(float base, float exponent) { return cephes_expf(exponent * 
 box2i boundingBox(const std::vector<box2i>& boxes);                                        // boxlist.d:16-28
 void boxSubtraction(const box2i& A, const box2i& C, box2i& D, box2i& E, box2i& F, box2i& G);  // boxlist.d:42-48
 void removeOverlappingAreas(std::vector<box2i>& boxes, std::vector<box2i>& filtered);      // boxlist.d:54-118
+// DirtyRectList.addRect, boxlist.d:236-292: the list stays free of overlaps (the mutex of the reference is left out:
+// the oracle is single-threaded)
+void dirtyRectListAdd(std::vector<box2i>& list, box2i rect);
 void tileAreas(const box2i* areas, int n, int maxW, int maxH, std::vector<box2i>& out);    // boxlist.d:139-167
 bool haveNoOverlap(const box2i* areas, int n);                                             // boxlist.d:171-186
 

@@ -265,6 +265,38 @@ void removeOverlappingAreas(std::vector<box2i>& boxes, std::vector<box2i>& filte
     }
 }
 
+void dirtyRectListAdd(std::vector<box2i>& list, box2i rect) {  // boxlist.d:236-292
+    if (rect.empty()) return;
+    bool processed = false;
+    for (int i = 0; i < (int)list.size(); ++i) {
+        box2i other = list[i];
+        if (other.contains(rect)) {  // candidate inside an element: discard it (boxlist.d:249-254)
+            processed = true;
+            break;
+        } else if (rect.contains(other)) {  // element inside the candidate: it goes (boxlist.d:255-260)
+            box2i last = list.back();
+            list.pop_back();
+            if (i < (int)list.size()) list[i] = last;
+            i--;
+        } else {
+            box2i common = other.intersection(rect);
+            if (!common.empty()) {  // keep `other` minus the common part (boxlist.d:263-280)
+                box2i D, E, F, G;
+                boxSubtraction(other, common, D, E, F, G);
+                box2i last = list.back();
+                list.pop_back();
+                if (i < (int)list.size()) list[i] = last;
+                i--;
+                if (!D.empty()) list.push_back(D);
+                if (!E.empty()) list.push_back(E);
+                if (!F.empty()) list.push_back(F);
+                if (!G.empty()) list.push_back(G);
+            }
+        }
+    }
+    if (!processed) list.push_back(rect);
+}
+
 void tileAreas(const box2i* areas, int n, int maxW, int maxH, std::vector<box2i>& out) {
     for (int k = 0; k < n; ++k) {
         const box2i& a = areas[k];

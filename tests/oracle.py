@@ -73,6 +73,7 @@ def lib():
             "b2ref_tile_areas": (I, [C.POINTER(box2i), I, I, I, C.POINTER(box2i), I]),
             "b2ref_remove_overlapping_areas": (I, [C.POINTER(box2i), I, C.POINTER(box2i), I]),
             "b2ref_bounding_box": (box2i, [C.POINTER(box2i), I]), "b2ref_have_no_overlap": (I, [C.POINTER(box2i), I]),
+            "b2ref_dirty_rect_list_add": (I, [C.POINTER(box2i), I, I, box2i]),
             "b2ref_impact_on_next_level": (box2i, [I, box2i, I, I]),
             "b2ref_linmap": (D, [D, D, D, D, D]), "b2ref_rsqrtss": (F, [F, I]), "b2ref_set_rsqrt_mode": (None, [I]),
             "b2ref_rsqrtss_table_vs_host": (C.c_long, []), "b2ref_pow_ps": (F, [F, F]), "b2ref_fastlog2": (F, [F]),
@@ -173,6 +174,20 @@ class Mipmap:
 
     def linearMipmapSample(self, level, x, y):
         return self._sample(self.l.b2ref_mip_linear_mipmap_sample, level, x, y, lvl_float=True)
+
+
+class DirtyRectList:
+    """DirtyRectList.addRect on a Python-held list (boxlist.d:236-292)"""
+
+    def __init__(self):
+        self.rects = []
+
+    def addRect(self, rect):
+        cap = len(self.rects) * 4 + 8
+        arr = (box2i * cap)(*[box2i(*r) for r in self.rects])
+        n = lib().b2ref_dirty_rect_list_add(arr, len(self.rects), cap, box2i(*rect))
+        assert n <= cap
+        self.rects = [arr[i].astuple() for i in range(n)]
 
 
 def draw_layer(dst, src, opacity, x, y, rects, mode):

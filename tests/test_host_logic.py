@@ -154,3 +154,52 @@ def test_default_params_match_reference_defaults(b2, oracle):
     assert bytes(p) == bytes(q)
     assert abs(p.light1_color[0] - 0.325) < 1e-6 and p.pass_active_mask == 0xff
     assert abs(p.light2_dir[1] - 0.99503719) < 1e-6
+
+
+def test_have_no_overlap_known_answer(b2, oracle):
+    # gui/dplug/gui/boxlist.d:188-192
+    assert b2.haveNoOverlap([(0, 0, 1, 1), (1, 1, 2, 2)])
+    assert not b2.haveNoOverlap([(0, 0, 1, 1), (0, 0, 2, 1)])
+    assert b2.haveNoOverlap([])
+
+
+def _coverage(rects, size=64):
+    m = np.zeros((size, size), dtype=np.int32)
+    for (x0, y0, x1, y1) in rects:
+        m[y0:y1, x0:x1] += 1
+    return m
+
+
+def test_dirty_rect_list_matches_reference_algorithm(b2, oracle):
+    """DirtyRectList.addRect (boxlist.d:236-292): same list, in the same order, as the restated reference algorithm;
+    the invariant (no overlaps) and the coverage (union of everything added) hold after every call."""
+    rng = np.random.default_rng(17)
+    for trial in range(30):
+        g, o = b2.DirtyRectList(), oracle.DirtyRectList()
+        assert g.isEmpty()
+        union = np.zeros((64, 64), dtype=bool)
+        for k in range(int(rng.integers(1, 25))):
+            x0, y0 = int(rng.integers(0, 60)), int(rng.integers(0, 60))
+            r = (x0, y0, int(rng.integers(x0, 65)), int(rng.integers(y0, 65)))   # may be empty: ignored (boxlist.d:241)
+            g.addRect(r); o.addRect(r)
+            union[r[1]:r[3], r[0]:r[2]] = True
+        assert g.isEmpty() == (len(o.rects) == 0)
+        got = g.pullAllRectangles()
+        assert got == o.rects
+        assert g.isEmpty() and g.pullAllRectangles() == []
+        cov = _coverage(got)
+        assert cov.max() <= 1 and b2.haveNoOverlap(got)
+        assert np.array_equal(cov > 0, union)
+
+
+def test_dirty_rect_list_cases(b2):
+    g = b2.DirtyRectList()
+    g.addRect((10, 10, 20, 20))
+    g.addRect((12, 12, 15, 15))            # inside an element: discarded
+    assert g.pullAllRectangles() == [(10, 10, 20, 20)]
+    g.addRect((12, 12, 15, 15)); g.addRect((10, 10, 20, 20))   # contains an element: the element goes
+    assert g.pullAllRectangles() == [(10, 10, 20, 20)]
+    g.addRect((0, 0, 10, 10)); g.addRect((5, 5, 15, 15))       # partial overlap: the old one is cut (above + left parts)
+    assert g.pullAllRectangles() == [(0, 0, 10, 5), (0, 5, 5, 10), (5, 5, 15, 15)]
+    with pytest.raises(b2.B2Error):
+        g.addRect((5, 5, 1, 1))            # unsorted (assert in the reference, boxlist.d:239)
