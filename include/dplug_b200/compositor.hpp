@@ -33,6 +33,28 @@ inline std::vector<box2i> tileAreas(const std::vector<box2i>& areas, int maxWidt
     return out;
 }
 
+inline bool haveNoOverlap(const std::vector<box2i>& areas) { return b2_have_no_overlap(areas.data(), (int)areas.size()) != 0; }  // boxlist.d:171-186
+
+// DirtyRectList, gui/dplug/gui/boxlist.d:200-303
+class DirtyRectList {
+public:
+    DirtyRectList() { check(b2_dirty_rects_create(&_h)); }
+    ~DirtyRectList() { b2_dirty_rects_destroy(_h); }
+    DirtyRectList(const DirtyRectList&) = delete;
+    DirtyRectList& operator=(const DirtyRectList&) = delete;
+    bool isEmpty() { return b2_dirty_rects_is_empty(_h) != 0; }
+    void addRect(box2i rect) { check(b2_dirty_rects_add(_h, rect)); }
+    void pullAllRectangles(std::vector<box2i>& result) {   // appends, like the reference (boxlist.d:224-234)
+        int n = b2_dirty_rects_pull_all(_h, nullptr, 0);
+        size_t at = result.size();
+        result.resize(at + (size_t)n);
+        b2_dirty_rects_pull_all(_h, result.data() + at, n);
+    }
+
+private:
+    b2_dirty_rects* _h = nullptr;
+};
+
 template <typename COLOR>
 class Mipmap {
 public:
@@ -56,6 +78,15 @@ public:
     }
     void generateLevel(int level, Quality q, box2i updateRect) { check(b2mip_generate_level(_h, level, (int)q, updateRect)); }
     void generateMipmaps(Quality q) { check(b2mip_generate_mipmaps(_h, (int)q)); }
+    // levels firstLevel .. firstLevel + qualities.size() - 1, the rectangle chained through impactOnNextLevel: what
+    // regenerateMipmaps does per dirty rectangle (graphics.d:1378-1419), in fused launches
+    std::vector<box2i> generateLevels(int firstLevel, const std::vector<Quality>& qualities, box2i updateRectPreviousLevel) {
+        std::vector<int> q(qualities.size());
+        for (size_t i = 0; i < q.size(); ++i) q[i] = (int)qualities[i];
+        std::vector<box2i> out(q.size());
+        check(b2mip_generate_levels(_h, firstLevel, (int)q.size(), q.data(), updateRectPreviousLevel, out.data()));
+        return out;
+    }
 
     void upload(int level, ImageRef<const COLOR> host, const std::vector<box2i>& rects) {
         check(b2mip_upload(_h, level, host.pixels, host.pitch, rects.data(), (int)rects.size()));

@@ -10,6 +10,14 @@
 int main(int argc, char** argv) {
     std::vector<b2::box2i> tiles = b2::tileAreas({b2::box2i{0, 0, 620, 330}}, 64, 64);
     if (tiles.size() != 60) { printf("tileAreas: %zu tiles\n", tiles.size()); return 1; }
+    {   // DirtyRectList (boxlist.d:200-303): host logic, works without a GPU
+        b2::DirtyRectList dirty;
+        dirty.addRect(b2::box2i{0, 0, 10, 10});
+        dirty.addRect(b2::box2i{5, 5, 15, 15});
+        std::vector<b2::box2i> pulled;
+        dirty.pullAllRectangles(pulled);
+        if (pulled.size() != 3 || !b2::haveNoOverlap(pulled) || !dirty.isEmpty()) { printf("DirtyRectList: %zu rects\n", pulled.size()); return 1; }
+    }
     const bool gpu = argc > 1 && !strcmp(argv[1], "gpu");
     if (!gpu) {
         if (b2_device_count() > 0) { printf("skip: a GPU is present\n"); return 0; }
