@@ -469,11 +469,47 @@ def run_c5(args, W, H, desc):
     tiles = b2.BoxArray(b2.tileAreas([(0, y0, W, y1)], 64, 64))
     whole = b2.BoxArray([(0, 0, W, H)])
 
+    own_rects, halo_rects = sh.own_and_halo_rects(W, H, y0, y1)
+    ia, ib = sh.interior_tile_rows(W, H, y0, y1)
+    own_rects, halo_rects = b2.BoxArray(own_rects), (b2.BoxArray(halo_rects) if halo_rects else None)
+    interior = b2.BoxArray(b2.tileAreas([(0, ia, W, ib)], 64, 64)) if ib > ia else None
+    edge_rects = [r for r in ((0, y0, W, ia), (0, ib, W, y1)) if r[3] > r[1]]
+    boundary = b2.BoxArray(b2.tileAreas(edge_rects, 64, 64)) if edge_rects else None
+    side = torch.cuda.Stream()
+    marks = []   # --breakdown: events between the phases of a step
+
+    def mark():
+        if args.breakdown:
+            e = torch.cuda.Event(enable_timing=True); e.record(stream); marks.append(e)
+
     def step():
+        mark()
         if world > 1:
-            sh.exchange_halos(rank, world, plan, stores, dist)
-        c.regenerateMipmaps(whole)
-        c.compositeTile(None, tiles)
+            # One exchange step per frame, hidden behind the work that does not depend on it: the halo rows travel while
+            # the mip rows that depend only on the band's own rows are generated and the interior tiles (those reading
+            # no halo row and no mip texel the halo pass writes) are composited; the mip texels that depend on a halo
+            # row are (re)generated on a second stream once the rows are there, then the boundary tiles follow.
+            reqs = sh.post_halo_exchange(rank, world, plan, stores, dist)
+            c.regenerateMipmaps(own_rects)
+            own_done = torch.cuda.Event(); own_done.record(stream)
+            mark()
+            if interior is not None:
+                c.compositeTile(None, interior)
+            mark()
+            with torch.cuda.stream(side):
+                side.wait_event(own_done)
+                sh.wait_halo_exchange(reqs)
+                if halo_rects is not None:
+                    c.regenerateMipmaps(halo_rects, stream=side.cuda_stream)
+                halo_done = torch.cuda.Event(); halo_done.record(side)
+            stream.wait_event(halo_done)
+            if boundary is not None:
+                c.compositeTile(None, boundary)
+        else:
+            c.regenerateMipmaps(whole)
+            mark()
+            c.compositeTile(None, tiles)
+        mark()
 
     def barrier():
         torch.cuda.synchronize()
@@ -496,6 +532,15 @@ def run_c5(args, W, H, desc):
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    if args.breakdown:
+        per = len(marks) // (args.steps + max(3, args.warmup))
+        last = marks[-per * args.steps:]
+        names = ["post exchange + mips (own rows)", "lighting (interior tiles)", "halo pass tail + lighting (boundary tiles)"] if world > 1 else ["mips", "lighting"]
+        acc = [0.0] * (per - 1)
+        for k in range(args.steps):
+            for j in range(per - 1):
+                acc[j] += last[k * per + j].elapsed_time(last[k * per + j + 1])
+        print("rank %d breakdown ms/step: %s" % (rank, ", ".join("%s %.3f" % (n, a / args.steps) for n, a in zip(names, acc))), file=sys.stderr, flush=True)
     if world > 1:
         t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     if rank == 0:
@@ -523,6 +568,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--instances", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="c5: per-phase device times of a step on stderr (every rank)")
     ap.add_argument("--c3-data", default="both", choices=["both", "random", "survey"])
     ap.add_argument("--mip-fusion", type=int, default=1, choices=[0, 1, 2],
                     help="0: one launch per generateLevel call; 1 (default): small levels fused; 2: every level fused")

@@ -187,9 +187,13 @@ class PBRCompositor:
         return Mipmap(RGBA8, 0, 0, 0, _handle=h) if h else None
 
     # --- GUIGraphics slice ----------------------------------------------------------------------
-    def regenerateMipmaps(self, rects):
-        """GUIGraphics.regenerateMipmaps — gui/dplug/gui/graphics.d:1354-1423."""
-        _lib.check(self._l.b2pbr_regenerate_mipmaps(self._h, _lib.boxes(rects), len(rects)))
+    def regenerateMipmaps(self, rects, stream=None):
+        """GUIGraphics.regenerateMipmaps — gui/dplug/gui/graphics.d:1354-1423.  `stream` (a raw CUDA stream handle):
+        enqueue on that stream instead of the compositor's."""
+        if stream is None:
+            _lib.check(self._l.b2pbr_regenerate_mipmaps(self._h, _lib.boxes(rects), len(rects)))
+        else:
+            _lib.check(self._l.b2pbr_regenerate_mipmaps_on(self._h, _lib.boxes(rects), len(rects), C.c_void_p(stream)))
 
     def compositeGUI(self, rectsToCompositeDisjointed, wfb=None):
         """GUIGraphics.compositeGUI — gui/dplug/gui/graphics.d:1338-1349."""

@@ -242,11 +242,12 @@ static int mipGenerateLevels(b2mip* m, int first, int n, const int* q, const b2_
         return B2_OK;
     }
     for (int k = 0; k < n;) {
-        // Large levels are bandwidth work and the lean one-launch-per-level kernels stream them best (measured: the
-        // fused kernel's region bookkeeping costs more issue slots than the saved HBM round trip is worth once a level
-        // has ~1 M texels).  Small levels are launch latency: they go through the fused kernel, up to three per launch.
-        const DevLevel& S = m->levels[first + k - 1];
-        if (!fuseAll && (long long)S.w * S.h > g_mipFuseBelow) {
+        // Large updates are bandwidth work and the lean one-launch-per-level kernels stream them best (measured: the
+        // fused kernel's region bookkeeping costs more issue slots than the saved HBM round trip is worth once a step
+        // reads ~1 M texels).  Small updates — small levels, or dirty rectangles of large ones — are launch latency:
+        // they go through the fused kernel, up to three levels per launch.
+        const long long srcTexels = (boxW(rects[k]) > 0 && boxH(rects[k]) > 0) ? 4ll * boxW(rects[k]) * boxH(rects[k]) : 0;
+        if (!fuseAll && srcTexels > g_mipFuseBelow) {
             int rc = mipGenerateLevel(m, first + k, q[k], rects[k]);
             if (rc) return rc;
             k += 1;
@@ -547,8 +548,13 @@ struct b2pbr {
     b2pbr_params params;
     uint32_t* dRsqrt = nullptr;
     float* dExpTab = nullptr;
-    Box* dBoxes = nullptr; int boxCap = 0;
-    Box* hBoxes = nullptr;           // pinned staging
+    // device work lists, cached per (area list, kind, strip cut): a caller that alternates between a few lists (the
+    // interior and the boundary tiles of a row band; a recorded graph and live calls) never re-uploads them
+    struct WorkList { std::vector<Box> key; int kind = -1, tail1 = 0, tail2 = 0; Box* d = nullptr; int cap = 0, n = 0; uint64_t used = 0; bool pinned = false; };
+    std::vector<WorkList> workLists;
+    uint64_t workClock = 0;
+    Box* dBoxes = nullptr;           // the current list (points into workLists)
+    Box* hBoxes = nullptr; int hBoxCap = 0;   // pinned staging
     cudaEvent_t boxCopied = nullptr;
     cudaStream_t sIn = nullptr, sOut = nullptr;   // copy streams of the pipelined host path
     std::vector<cudaGraphExec_t> graphs;          // frames recorded with b2pbr_graph_begin / _end
@@ -558,10 +564,8 @@ struct b2pbr {
     cudaStream_t sAux = nullptr;                  // the depth pyramid is regenerated next to the diffuse one
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     std::vector<cudaEvent_t> pipeEvents;
-    std::vector<Box> lastBoxes;
-    int lastBoxKind = -1;            // what dBoxes holds: 0 = the caller's areas, 1 = 32-column strips of them
-    int tailRow = 1 << 30, lastTailRow = 1 << 30;   // areas ending below this row are cut into 8-row strips (pipelined host call)
-    int tailRow2 = 1 << 30, lastTailRow2 = 1 << 30; // ... and below this one into 4-row strips
+    int tailRow = 1 << 30;           // areas ending below this row are cut into 8-row strips (pipelined host call)
+    int tailRow2 = 1 << 30;          // ... and below this one into 4-row strips
     int nDeviceBoxes = 0;
     int mode = B2_MODE_FAST;
     uint64_t launches = 0;
@@ -707,9 +711,14 @@ static int stripRowsFor(const b2_box2i* areas, int n) {
 // into warp-sized strips of 32 columns x strip_rows rows for k_pbr_fast.  The list is kept on the device and
 // re-used while the caller passes the same areas (a full-frame tile list never changes between frames).
 static int pbrUploadBoxes(b2pbr* c, const b2_box2i* areas, int n, int kind) {
-    bool same = c->lastBoxKind == kind && c->lastTailRow == c->tailRow && c->lastTailRow2 == c->tailRow2 && (int)c->lastBoxes.size() == n && n > 0 &&
-                memcmp(c->lastBoxes.data(), areas, sizeof(Box) * n) == 0;
-    if (same) return B2_OK;
+    for (auto& wl : c->workLists)
+        if (wl.kind == kind && wl.tail1 == c->tailRow && wl.tail2 == c->tailRow2 && (int)wl.key.size() == n && n > 0 &&
+            memcmp(wl.key.data(), areas, sizeof(Box) * n) == 0) {
+            wl.used = ++c->workClock;
+            if (c->capturing) wl.pinned = true;   // a recorded graph reads this list at every replay
+            c->dBoxes = wl.d; c->nDeviceBoxes = wl.n;
+            return B2_OK;
+        }
     if (c->capturing) return fail(B2_ERR_STATE, "graph capture: composite this area list once before recording it (its work list is uploaded then)");
     std::vector<Box> work;
     if (kind == 0) work.assign((const Box*)areas, (const Box*)areas + n);
@@ -724,24 +733,36 @@ static int pbrUploadBoxes(b2pbr* c, const b2_box2i* areas, int n, int kind) {
         }
     }
     const int m = (int)work.size();
-    if (m > c->boxCap) {
-        int cap = m < 16384 ? 16384 : m * 2;
-        if (c->dBoxes) { CU(cudaStreamSynchronize(c->stream)); cudaFree(c->dBoxes); cudaFreeHost(c->hBoxes); c->dBoxes = nullptr; c->hBoxes = nullptr; }
-        CU(cudaMalloc((void**)&c->dBoxes, sizeof(Box) * cap));
-        CU(cudaMallocHost((void**)&c->hBoxes, sizeof(Box) * cap));
-        c->boxCap = cap;
+    // slot: a free one (up to 4), else the least recently used that no graph refers to, else a new one
+    b2pbr::WorkList* slot = nullptr;
+    if (c->workLists.size() < 4) { c->workLists.emplace_back(); slot = &c->workLists.back(); }
+    else {
+        for (auto& wl : c->workLists)
+            if (!wl.pinned && (!slot || wl.used < slot->used)) slot = &wl;
+        if (!slot) { c->workLists.emplace_back(); slot = &c->workLists.back(); }
+    }
+    if (m > slot->cap) {
+        const int cap = m < 16384 ? 16384 : m * 2;
+        if (slot->d) { CU(cudaStreamSynchronize(c->stream)); cudaFree(slot->d); slot->d = nullptr; }
+        CU(cudaMalloc((void**)&slot->d, sizeof(Box) * cap));
+        slot->cap = cap;
+    }
+    if (m > c->hBoxCap) {
+        CU(cudaEventSynchronize(c->boxCopied));
+        if (c->hBoxes) cudaFreeHost(c->hBoxes);
+        c->hBoxCap = m < 16384 ? 16384 : m * 2;
+        CU(cudaMallocHost((void**)&c->hBoxes, sizeof(Box) * c->hBoxCap));
     }
     if (m > 0) {
         CU(cudaEventSynchronize(c->boxCopied));  // staging buffer free again?
         memcpy(c->hBoxes, work.data(), sizeof(Box) * m);
-        CU(cudaMemcpyAsync(c->dBoxes, c->hBoxes, sizeof(Box) * m, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(slot->d, c->hBoxes, sizeof(Box) * m, cudaMemcpyHostToDevice, c->stream));
         CU(cudaEventRecord(c->boxCopied, c->stream));
     }
-    c->lastBoxes.assign((const Box*)areas, (const Box*)areas + n);
-    c->lastBoxKind = kind;
-    c->lastTailRow = c->tailRow;
-    c->lastTailRow2 = c->tailRow2;
-    c->nDeviceBoxes = m;
+    slot->key.assign((const Box*)areas, (const Box*)areas + n);
+    slot->kind = kind; slot->tail1 = c->tailRow; slot->tail2 = c->tailRow2;
+    slot->n = m; slot->used = ++c->workClock;
+    c->dBoxes = slot->d; c->nDeviceBoxes = m;
     return B2_OK;
 }
 
@@ -874,7 +895,8 @@ void b2pbr_destroy(b2pbr* c) {
     if (c->dLut) cudaFree(c->dLut);
     if (c->dRsqrt) cudaFree(c->dRsqrt);
     if (c->dExpTab) cudaFree(c->dExpTab);
-    if (c->dBoxes) cudaFree(c->dBoxes);
+    for (auto& wl : c->workLists)
+        if (wl.d) cudaFree(wl.d);
     if (c->hBoxes) cudaFreeHost(c->hBoxes);
     if (c->boxCopied) cudaEventDestroy(c->boxCopied);
     for (auto g : c->graphs) if (g) cudaGraphExecDestroy(g);
@@ -904,8 +926,7 @@ int b2pbr_resize(b2pbr* c, int width, int height, int tw, int th) {
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     pbrFreeMaps(c);
-    c->lastBoxes.clear();
-    c->lastBoxKind = -1;
+    for (auto& wl : c->workLists) { wl.key.clear(); wl.kind = -1; wl.pinned = false; }   // strip cuts depend on the size
     c->W = width; c->H = height; c->tileW = tw; c->tileH = th;
     int y0 = 0, y1 = height, dUp = 0, dDown = 0, zUp = 0, zDown = 0;
     if (c->banded) {
@@ -1060,6 +1081,17 @@ int b2pbr_regenerate_mipmaps(b2pbr* c, const b2_box2i* rects, int n) {
     if (err) return err;
     c->launches += c->diffuse->launches + c->depth->launches - before;
     return B2_OK;
+}
+
+int b2pbr_regenerate_mipmaps_on(b2pbr* c, const b2_box2i* rects, int n, void* cuda_stream) {
+    if (!c || !c->diffuse) return fail(B2_ERR_STATE, "regenerateMipmaps before resize");
+    // same work, enqueued on the caller's stream (no synchronisation): the caller orders it against the compositor's
+    // own stream with events (multi-GPU: the halo rows' mips run beside the lighting of the tiles that do not read them)
+    cudaStream_t keep = c->stream, keepD = c->diffuse->stream, keepZ = c->depth->stream;
+    c->stream = c->diffuse->stream = c->depth->stream = (cudaStream_t)cuda_stream;
+    const int rc = b2pbr_regenerate_mipmaps(c, rects, n);
+    c->stream = keep; c->diffuse->stream = keepD; c->depth->stream = keepZ;
+    return rc;
 }
 
 int b2pbr_composite_tile(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, b2mip* material, b2mip* depth) {

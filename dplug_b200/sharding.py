@@ -56,10 +56,12 @@ def halo_plan(W, H, world, align=64):
     return bands, plan
 
 
-def exchange_halos(rank, world, plan, stores, dist):
-    """Executes the plan.  `stores[map] = (tensor2d, first_row)`: a (rows, pitch_bytes) uint8 torch tensor viewing
-    the rows this rank stores for level 0 of `map` (global row `first_row` first).  Sends are derived from the
-    other ranks' receive lists, so every rank posts matching isend / irecv pairs in one batch."""
+def post_halo_exchange(rank, world, plan, stores, dist):
+    """Starts the exchange of the plan and returns the pending requests.  `stores[map] = (tensor2d, first_row)`: a
+    (rows, pitch_bytes) uint8 torch tensor viewing the rows this rank stores for level 0 of `map` (global row
+    `first_row` first).  Sends are derived from the other ranks' receive lists, so every rank posts matching
+    isend / irecv pairs in one batch.  Only halo rows (rows outside the band) are written, so work that reads the
+    band's own rows — `regenerateMipmaps(own_and_halo_rects(...)[0])` — may run while the rows are in flight."""
     ops = []
     for dst in range(world):
         for (which, src, lo, hi) in plan[dst]:
@@ -69,7 +71,74 @@ def exchange_halos(rank, world, plan, stores, dist):
             if dst == rank and src != rank:
                 t, first = stores[which]
                 ops.append(dist.P2POp(dist.irecv, t[lo - first:hi - first], src))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-    return len(ops)
+    return dist.batch_isend_irecv(ops) if ops else []
+
+
+def wait_halo_exchange(reqs):
+    for req in reqs:
+        req.wait()
+    return len(reqs)
+
+
+def exchange_halos(rank, world, plan, stores, dist):
+    """Executes the plan and waits for it; returns the number of point-to-point operations of this rank."""
+    return wait_halo_exchange(post_halo_exchange(rank, world, plan, stores, dist))
+
+
+def own_and_halo_rects(W, H, y0, y1):
+    """Update rectangles of a band's frame in two steps: ([own rows], [halo rows above, halo rows below]).
+    regenerateMipmaps(own) followed — once the halos have arrived — by regenerateMipmaps(halo) leaves every pyramid
+    level exactly as one regenerateMipmaps over everything would: the second call recomputes, through the
+    impactOnNextLevel chain, every mip texel that depends on a halo row (the same argument that makes the reference's
+    dirty-rectangle updates correct, gui/dplug/gui/graphics.d:1378-1419)."""
+    lo, hi = need_rows(W, H, y0, y1, DIFFUSE, 0)      # the widest halo (level-5 bicubic bloom, SURVEY Appendix C)
+    halos = []
+    if lo < y0:
+        halos.append((0, lo, W, y0))
+    if hi > y1:
+        halos.append((0, y1, W, hi))
+    return [(0, y0, W, y1)], halos
+
+
+_RECIPES = {DIFFUSE: (2, 1, 1, 1, 1), DEPTH: (0, 0, 1, 1)}   # qualities of levels 1.. (gui/dplug/gui/graphics.d:1380-1384, 1414)
+
+
+def _rows_written(W, H, rect, which):
+    """rows [lo, hi) of levels 1.. that regenerateMipmaps([rect]) writes (the impactOnNextLevel chain)"""
+    from .boxlist import impactOnNextLevel
+    out, area, w, h = [], rect, W, H
+    for q in _RECIPES[which]:
+        if w >> 1 == 0 or h >> 1 == 0:
+            break
+        area = impactOnNextLevel(q, area, w, h)
+        out.append((area[1], area[3]))
+        w, h = w >> 1, h >> 1
+    return out
+
+
+def interior_tile_rows(W, H, y0, y1, align=64):
+    """Rows [a, b) of a band (whole GUI tiles) whose compositing reads neither a level-0 halo row nor a mip texel that
+    regenerateMipmaps(halo rectangles) writes: these tiles can be composited after regenerateMipmaps(own rows) while
+    the halo rows are still in flight and while the halo pass runs on another stream; the rest of the band
+    ([y0, a) and [b, y1)) follows once the halo pass is done."""
+    _, halos = own_and_halo_rects(W, H, y0, y1)
+    a, b = y0, y1
+    for rect in halos:
+        top = rect[1] < y0
+        written = {which: _rows_written(W, H, rect, which) for which in (DIFFUSE, DEPTH)}
+        while a < b:
+            cand = (a, min(a + align, b)) if top else (max(b - align, a), b)
+            clash = False
+            for which in (DIFFUSE, DEPTH):
+                lo0, hi0 = need_rows(W, H, cand[0], cand[1], which, 0)
+                clash = clash or lo0 < y0 or hi0 > y1
+                for level, (wlo, whi) in enumerate(written[which], 1):
+                    nlo, nhi = need_rows(W, H, cand[0], cand[1], which, level)
+                    clash = clash or (nlo < whi and wlo < nhi)
+            if not clash:
+                break
+            if top:
+                a = cand[1]
+            else:
+                b = cand[0]
+    return a, b

@@ -180,6 +180,8 @@ int b2pbr_output(b2pbr*, b2_imageref* out);
  * _rectsToUpdateDisjointedPBR: diffuse level 1 boxAlphaCovIntoPremul, levels 2..5 cubic; depth border
  * (replicateBordersTouching == clamp-to-edge addressing on the device), depth levels 1,2 box, 3,4 cubic. */
 int b2pbr_regenerate_mipmaps(b2pbr*, const b2_box2i* rects, int n);
+/* the same, enqueued on `cuda_stream` instead of the compositor's stream (no synchronisation; order it with events) */
+int b2pbr_regenerate_mipmaps_on(b2pbr*, const b2_box2i* rects, int n, void* cuda_stream);
 
 /* ICompositor.compositeTile(wfb, areas, diffuseMap, materialMap, depthMap, profiler) —
  * compositor.d:63-68, legacypbr.d:201-260 — on device-resident maps; writes the composited twin.

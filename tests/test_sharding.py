@@ -68,6 +68,24 @@ def test_need_rows_vs_brute_force(b2, H, y0, y1):
         assert sh.need_rows(W, H, y0, y1, sh.DIFFUSE, l) == want[l], l
 
 
+def test_interior_tile_rows(b2):
+    """host arithmetic: the tiles a band may composite before its halos exist (bench.py --workload c5)"""
+    from dplug_b200 import sharding as sh
+    W = H = 16384
+    bands, _ = sh.halo_plan(W, H, 8)
+    for r, (y0, y1) in enumerate(bands):
+        a, b = sh.interior_tile_rows(W, H, y0, y1)
+        assert (a == y0) == (r == 0) and (b == y1) == (r == 7)
+        assert 0 <= a - y0 <= 256 and 0 <= y1 - b <= 256 and (a - y0) % 64 == 0 and (y1 - b) % 64 == 0
+        # nothing the interior reads is a halo row
+        for which in (sh.DIFFUSE, sh.DEPTH):
+            lo, hi = sh.need_rows(W, H, a, b, which, 0)
+            assert y0 <= lo and hi <= y1
+    # a band thinner than two bloom reaches has no interior
+    a, b = sh.interior_tile_rows(256, 1024, 320, 448)
+    assert a == b
+
+
 _WORKER = r'''
 import os, sys
 sys.path.insert(0, %(root)r)
@@ -151,3 +169,32 @@ def test_banded_composite_equals_unbanded(b2, mode, world):
         for l in range(1, 6):
             _, _, lo, hi = c.bandRows(sh.DIFFUSE, l)
             assert np.array_equal(c.diffuseMap.downloadRows(l, lo, hi), ref.diffuseMap.download(l)[lo:hi]), l
+        # the overlapped order of bench.py --workload c5: the band's own rows are regenerated while the halo rows are
+        # still in flight (poisoned here), the halo rectangles afterwards
+        c2 = b2.PBRCompositor(0, band=(y0, y1))
+        c2.resizeBuffers(W, H)
+        c2.setMode(mode)
+        c2.setSkybox(sky)
+        own, halos = sh.own_and_halo_rects(W, H, y0, y1)
+        for which, img in ((sh.DIFFUSE, d), (sh.MATERIAL, m), (sh.DEPTH, z)):
+            slo, shi, lo, hi = c2.bandRows(which, 0)
+            poison = np.full_like(img[lo:hi], 0xAB)
+            poison[y0 - lo:y1 - lo] = img[y0:y1]
+            c2.map(which).uploadRows(0, poison, lo)
+        c2.regenerateMipmaps(own)
+        ia, ib = sh.interior_tile_rows(W, H, y0, y1)
+        assert y0 <= ia <= ib <= y1 and (ia - y0) % 64 == 0 and (r != 0 or ia == y0) and (r != world - 1 or ib == y1 or ib == ia)
+        if ib > ia:
+            c2.compositeGUI([(0, ia, W, ib)])                    # interior tiles: before the halos exist
+        for which, img in ((sh.DIFFUSE, d), (sh.MATERIAL, m), (sh.DEPTH, z)):
+            slo, shi, lo, hi = c2.bandRows(which, 0)
+            c2.map(which).uploadRows(0, img[lo:hi], lo)          # "the halos arrive"
+        if halos:
+            c2.regenerateMipmaps(halos)
+        edge = [rc for rc in ((0, y0, W, ia), (0, ib, W, y1)) if rc[3] > rc[1]]
+        if edge:
+            c2.compositeGUI(edge)
+        assert np.array_equal(c2.downloadRows(y0, y1), want[y0:y1]), ("overlapped", r, y0, y1)
+        for l in range(1, 6):
+            _, _, lo, hi = c2.bandRows(sh.DIFFUSE, l)
+            assert np.array_equal(c2.diffuseMap.downloadRows(l, lo, hi), ref.diffuseMap.download(l)[lo:hi]), ("overlapped", l)
