@@ -186,6 +186,7 @@ def run_b200(args, W, H, desc):
     sky = synth.skybox()
     comps, hosts = [], []
     distinct = {}
+    streams = [torch.cuda.Stream() for _ in range(args.batch_streams)] if batch else []
     for k in range(R):
         seed = synth.SEED + 1000 * rank + (k % 8 if batch else k)   # the batch re-uses 8 distinct synthetic UIs per rank
         if seed not in distinct:
@@ -193,7 +194,9 @@ def run_b200(args, W, H, desc):
         d, m, z = distinct[seed]
         c = b2.PBRCompositor(local)
         c.resizeBuffers(W, H, 64, 64)
-        c.set_stream(stream.cuda_stream)
+        # the batch: independent UIs are dealt over a few streams, so one UI's small mip launches and the tail of its
+        # lighting kernel overlap the next UI's work
+        c.set_stream((streams[k % len(streams)] if batch else stream).cuda_stream)
         c.setSkybox(sky)
         c.diffuseMap.upload(0, d); c.materialMap.upload(0, m); c.depthMap.upload(0, z)
         comps.append(c)
@@ -205,8 +208,13 @@ def run_b200(args, W, H, desc):
 
     def step(i):
         if batch:
+            fork = torch.cuda.Event(); fork.record(stream)
+            for st in streams:
+                st.wait_event(fork)
             for k in range(R):
                 one(k)
+            for st in streams:
+                join = torch.cuda.Event(); join.record(st); stream.wait_event(join)
         else:
             one(i % R)
 
@@ -259,14 +267,17 @@ def run_b200(args, W, H, desc):
     # frame sequence (the mip regeneration of the same frame runs before it, untimed, so the cache state is the
     # timed region's)
     evs = []
-    for i in range(min(args.steps, 200)):
+    for i in range(min(max(args.steps, 20) if batch else args.steps, 200)):
         c = comps[i % R]
+        st = streams[(i % R) % len(streams)] if batch else stream   # the stream this compositor launches on
         c.regenerateMipmaps(whole)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
+        a.record(st)
         c.compositeTile(None, tiles)
-        b.record(stream)
+        b.record(st)
         evs.append((a, b))
+        if batch:
+            torch.cuda.synchronize()     # timed alone, not next to another stream's frame
     torch.cuda.synchronize()
     light_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
 
@@ -311,7 +322,7 @@ def run_b200(args, W, H, desc):
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong" if batch else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (8 distinct UIs per GPU, re-used across the batch)" if batch else "synthetic",
-        "config": {"workload": desc, "tile": "64x64", "instances_per_gpu": R, "cuda_graph": bool(args.graph),
+        "config": {"workload": desc, "tile": "64x64", "instances_per_gpu": R, "cuda_graph": bool(args.graph), **({"streams": len(streams)} if batch else {}),
                    "l2": "inputs larger than L2: %d independent frames (%.0f MB) visited round-robin" % (R, R * B / 1e6),
                    "parallelism": "independent frames per GPU, no collective" if world > 1 else "1 GPU"},
         "frame_roofline_frac": (B * (R if batch else 1) * args.steps / (ms * 1e-3) / 1e9) / peak,
@@ -568,6 +579,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--instances", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch-streams", type=int, default=4, help="c4: streams the batch's independent UIs are dealt over")
     ap.add_argument("--breakdown", action="store_true", help="c5: per-phase device times of a step on stderr (every rank)")
     ap.add_argument("--c3-data", default="both", choices=["both", "random", "survey"])
     ap.add_argument("--mip-fusion", type=int, default=1, choices=[0, 1, 2],

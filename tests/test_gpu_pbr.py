@@ -60,6 +60,23 @@ def test_full_frame_parity(b2, oracle, W, H, kind, mode):
         assert frac < 0.02, "fast kernel: %.4f of channels differ by 1 LSB (expected a truncation-boundary trickle)" % frac
 
 
+@pytest.mark.parametrize("W,H,rows", [(1024, 768, 8), (1600, 1200, 16), (2048, 1024, 16)])
+def test_strip_heights(b2, oracle, W, H, rows):
+    """The throughput kernel cuts the tiles into warp strips whose height depends on the canvas size (4 rows at 620x330
+    above, 32 at 4K below; 8 and 16 here, and 2048x1024 is BASELINE config 4's UI size): the output must not depend
+    on the cut — fast vs the oracle within 1 LSB, and identical to the same frame composited band by band."""
+    comp, ref, _ = _setup(b2, oracle, W, H, "smooth", mode=0)
+    whole = [(0, 0, W, H)]
+    comp.regenerateMipmaps(whole)
+    comp.compositeGUI(whole)
+    got = comp.download()
+    _compare(got, ref.fullFrame(), "%dx%d, %d-row strips" % (W, H, rows))
+    # a different area list (three horizontal slabs -> other strip heights near their edges) gives the same bytes
+    comp.compositeGUI([(0, 0, W, 192)]); a = comp.download()[:192].copy()
+    comp.compositeGUI([(0, 192, W, H)]); b = comp.download()[192:].copy()
+    assert np.array_equal(np.concatenate([a, b]), got)
+
+
 def test_distort_lighting_overrides(b2, oracle):
     """examples/distort/source/gui.d:41-48 light set-up at its default 620x330 size (BASELINE config 1)."""
     import ctypes as C
