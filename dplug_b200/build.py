@@ -19,7 +19,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-ftz=false",
 UNITS = [
     ("b2pbr.cu", ["-fmad=false"]),
     ("mip_kernels.cu", ["-fmad=false"]),
-    ("mip_fused.cu", ["-fmad=false"]),
+    ("mip_fused.cu", ["-fmad=false"] + (["-DB2_MIP_DEBUG"] if os.environ.get("B2_MIP_DEBUG") else [])),
     ("pbr_exact.cu", ["-fmad=false"]),
     ("pbr_fast.cu", ["-DB2_MIN_CTAS=%s" % os.environ.get("B2_MIN_CTAS", "4")]),
 ]

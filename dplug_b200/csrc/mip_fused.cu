@@ -10,6 +10,7 @@
 // (what the next generateLevel call of the chain would read), so the result does not depend on the pyramid having
 // been consistent outside the rectangles.  All arithmetic is the per-level kernels' (mip_math.cuh): integer paths
 // bit-exact, the alpha-premultiplying box in single IEEE operations (this file is compiled with -fmad=false).
+#include <cstdio>
 #include "mip_math.cuh"
 
 namespace b2 {
@@ -34,8 +35,21 @@ __device__ __forceinline__ bool inBox(const Box& b, int x, int y) { return x >= 
 template <typename T>
 struct Region {
     T* p; int x0, y0, stride;
+#ifdef B2_MIP_DEBUG   // bounds-checked build (python dplug_b200/build.py with B2_MIP_DEBUG=1): traps on any access outside the buffer
+    int rowsCap;
+    __device__ __forceinline__ T& at(int x, int y) const {
+        if (x < x0 || x - x0 >= stride || y < y0 || y - y0 >= rowsCap) { printf("mip_fused: (%d,%d) outside region x0=%d y0=%d %dx%d\n", x, y, x0, y0, stride, rowsCap); __trap(); }
+        return p[(y - y0) * stride + (x - x0)];
+    }
+#else
     __device__ __forceinline__ T& at(int x, int y) const { return p[(y - y0) * stride + (x - x0)]; }
+#endif
 };
+#ifdef B2_MIP_DEBUG
+#define B2_REGION(T, buf, x0, y0, stride, rows) Region<T>{buf, x0, y0, stride, rows}
+#else
+#define B2_REGION(T, buf, x0, y0, stride, rows) Region<T>{buf, x0, y0, stride}
+#endif
 template <typename T>
 struct GlobalSrc {
     const DevLevel& L;
@@ -251,6 +265,9 @@ __device__ __forceinline__ void stepFromShared(int q, const Region<T>& in, int s
         if (sizeof(T) == 4 && q == Q_CUBIC && rowUpd && x >= fastLo && x <= fastHi) {
             // two adjacent texels share four of their six source columns 2x-1 .. 2x+4
             const T* col = in.p + (2 * x - in.x0);                   // (2x - in.x0) is even: 64-bit aligned rows
+#ifdef B2_MIP_DEBUG
+            (void)in.at(2 * x - 1, max(2 * y - 1, 0)); (void)in.at(2 * x + 4, min(2 * y + 2, sh - 1));
+#endif
             const int ys[4] = {max(2 * y - 1, 0), 2 * y, 2 * y + 1, min(2 * y + 2, sh - 1)};
             uint32_t c[6][4];
 #pragma unroll
@@ -315,10 +332,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_mip_fused(const __grid_con
         compY[k - 1] = ivUnion(ownY[k - 1], ivNeed(A.q[k - 1], compY[k], A.lv[k - 1].h));
     }
     constexpr int G = sizeof(T) == 4 ? 2 : 4;
-    const Region<T> r1{buf1, compX[1].a & ~(G - 1), compY[1].a, B1W};
+    const Region<T> r1 = B2_REGION(T, buf1, compX[1].a & ~(G - 1), compY[1].a, B1W, B1H);
     if (STAGE0) {
         const Iv sx = ivNeed(A.q[0], compX[1], A.lv[0].w), sy = ivNeed(A.q[0], compY[1], A.lv[0].h);
-        const Region<T> r0{buf0, sx.a & ~1, sy.a, B0W};
+        const Region<T> r0 = B2_REGION(T, buf0, sx.a & ~1, sy.a, B0W, B0H);
         stageRegion<T>(A.lv[0], sx, sy, r0);
         __syncthreads();
         stepFromShared<T>(A.q[0], r0, A.lv[0].w, A.lv[0].h, A.lv[1], A.upd[0], ownX[1], ownY[1], compX[1], compY[1], N > 1, r1);
@@ -326,7 +343,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_mip_fused(const __grid_con
         stepFromGlobal<T>(A.q[0], A.lv[0], A.lv[1], A.upd[0], ownX[1], ownY[1], compX[1], compY[1], N > 1, r1, A.negZero2);
     }
     if (N >= 2) {
-        const Region<T> r2{buf2, compX[2].a & ~1, compY[2].a, B2W};
+        const Region<T> r2 = B2_REGION(T, buf2, compX[2].a & ~1, compY[2].a, B2W, B2H);
         __syncthreads();
         stepFromShared<T>(A.q[1], r1, A.lv[1].w, A.lv[1].h, A.lv[2], A.upd[1], ownX[2], ownY[2], compX[2], compY[2], N > 2, r2);
         if (N >= 3) {
