@@ -142,6 +142,82 @@ __global__ void __launch_bounds__(256) k_cubic_rgba(DevLevel dst, DevLevel src, 
     }
 }
 
+// Wide variant for large rectangles: thread = 4 destination texels (x a multiple of 4), two 128-bit loads per source
+// row; the addressing, the edge predicates and the two neighbour columns (warp shuffles) are paid once per four
+// texels instead of once per two.  Same integer arithmetic, same bytes.
+__global__ void __launch_bounds__(256) k_cubic_rgba4(DevLevel dst, DevLevel src, Box r) {
+    const int xq = (r.minx >> 2) + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = r.miny + blockIdx.y * blockDim.y + threadIdx.y;  // uniform per warp (blockDim.x == 32)
+    if (y >= r.maxy) return;
+    const int x = xq * 4;
+    const int sw = src.w, sh = src.h;
+    const uint32_t* rows[4] = {rowPtr<uint32_t>(src, max(2 * y - 1, 0)), rowPtr<uint32_t>(src, 2 * y), rowPtr<uint32_t>(src, 2 * y + 1),
+                               rowPtr<uint32_t>(src, min(2 * y + 2, sh - 1))};
+    uint32_t lo[10], hi[10];   // columns 2x-1 .. 2x+8
+    const bool active = x < r.maxx && x + 3 >= r.minx && 2 * x < sw;
+    const bool vec = active && (2 * x + 7 < sw);
+    if (vec) {
+        uint4 a[4], b[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            a[k] = __ldg(reinterpret_cast<const uint4*>(rows[k] + 2 * x));
+            b[k] = __ldg(reinterpret_cast<const uint4*>(rows[k] + 2 * x + 4));
+        }
+        vsumRGBA(a[0].x, a[1].x, a[2].x, a[3].x, lo[1], hi[1]);
+        vsumRGBA(a[0].y, a[1].y, a[2].y, a[3].y, lo[2], hi[2]);
+        vsumRGBA(a[0].z, a[1].z, a[2].z, a[3].z, lo[3], hi[3]);
+        vsumRGBA(a[0].w, a[1].w, a[2].w, a[3].w, lo[4], hi[4]);
+        vsumRGBA(b[0].x, b[1].x, b[2].x, b[3].x, lo[5], hi[5]);
+        vsumRGBA(b[0].y, b[1].y, b[2].y, b[3].y, lo[6], hi[6]);
+        vsumRGBA(b[0].z, b[1].z, b[2].z, b[3].z, lo[7], hi[7]);
+        vsumRGBA(b[0].w, b[1].w, b[2].w, b[3].w, lo[8], hi[8]);
+    } else if (active) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int cx = min(2 * x + k, sw - 1);
+            vsumRGBA(__ldg(rows[0] + cx), __ldg(rows[1] + cx), __ldg(rows[2] + cx), __ldg(rows[3] + cx), lo[1 + k], hi[1 + k]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 1; k <= 8; ++k) lo[k] = hi[k] = 0;
+    }
+    // neighbours: column 2x-1 = left lane's column index 8, column 2x+8 = right lane's column index 1
+    const unsigned full = 0xffffffffu;
+    const uint32_t lLo = __shfl_up_sync(full, lo[8], 1), lHi = __shfl_up_sync(full, hi[8], 1);
+    const uint32_t rLo = __shfl_down_sync(full, lo[1], 1), rHi = __shfl_down_sync(full, hi[1], 1);
+    const bool leftOk = __shfl_up_sync(full, (int)vec, 1) && threadIdx.x > 0;
+    const bool rightOk = __shfl_down_sync(full, (int)active, 1) && threadIdx.x < 31;
+    if (!active) return;
+    if (leftOk) { lo[0] = lLo; hi[0] = lHi; }
+    else {
+        const int cx = max(2 * x - 1, 0);
+        vsumRGBA(__ldg(rows[0] + cx), __ldg(rows[1] + cx), __ldg(rows[2] + cx), __ldg(rows[3] + cx), lo[0], hi[0]);
+    }
+    if (rightOk && 2 * x + 8 < sw) { lo[9] = rLo; hi[9] = rHi; }
+    else {
+        const int cx = min(2 * x + 8, sw - 1);
+        vsumRGBA(__ldg(rows[0] + cx), __ldg(rows[1] + cx), __ldg(rows[2] + cx), __ldg(rows[3] + cx), lo[9], hi[9]);
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        // destination x+t: columns 2(x+t)-1 .. 2(x+t)+2 = local indices 2t .. 2t+3; the right-most tap is clamped to
+        // the last source column (mipmap.d:934-935)
+        uint32_t l3 = lo[2 * t + 3], h3 = hi[2 * t + 3];
+        if (2 * (x + t) + 2 > sw - 1) { l3 = lo[2 * t + 2]; h3 = hi[2 * t + 2]; }
+        const uint32_t sl = (lo[2 * t] + l3) + 3u * (lo[2 * t + 1] + lo[2 * t + 2]) + 0x00200020u;
+        const uint32_t sh2 = (hi[2 * t] + h3) + 3u * (hi[2 * t + 1] + hi[2 * t + 2]) + 0x00200020u;
+        o[t] = ((sl >> 6) & 0x00ff00ffu) | (((sh2 >> 6) & 0x00ff00ffu) << 8);
+    }
+    uint32_t* d = rowPtrW<uint32_t>(dst, y);
+    if (x >= r.minx && x + 3 < r.maxx) *reinterpret_cast<uint4*>(d + x) = make_uint4(o[0], o[1], o[2], o[3]);
+    else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (x + t >= r.minx && x + t < r.maxx) d[x + t] = o[t];
+    }
+}
+
 // L16 variant: thread = 2 destination texels; vertical sums are 32-bit per column (<= 8*65535).
 __global__ void __launch_bounds__(256) k_cubic_l16(DevLevel dst, DevLevel src, Box r) {
     const int xp = (r.minx >> 1) + blockIdx.x * blockDim.x + threadIdx.x;
@@ -316,6 +392,11 @@ void launch_box_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_
 }
 void launch_cubic_rgba(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s) {
     dim3 block(32, 8);
+    if (r.maxx - r.minx >= 256) {   // wide rectangles: four texels per thread
+        int quads = ((r.maxx + 3) >> 2) - (r.minx >> 2);
+        k_cubic_rgba4<<<gridFor(quads, r.maxy - r.miny, block), block, 0, s>>>(dst, src, r);
+        return;
+    }
     int pairs = ((r.maxx + 1) >> 1) - (r.minx >> 1);
     k_cubic_rgba<<<gridFor(pairs, r.maxy - r.miny, block), block, 0, s>>>(dst, src, r);
 }

@@ -50,6 +50,25 @@ def test_generate_next_level_dirty_rects(b2, oracle, color, quality):
         assert np.array_equal(g.download(1), o.download(1)), r
 
 
+def test_cubic_wide_rectangles(b2, oracle):
+    """Rectangles at least 256 texels wide take the four-texels-per-thread cubic kernel: ragged left / right edges,
+    the clamped taps at both image borders, odd source width."""
+    rng = np.random.default_rng(31)
+    w, h = 1301, 97
+    src = _rand(rng, 0, w, h)
+    g, o = b2.Mipmap(0, 1, w, h), oracle.Mipmap(0, 1, w, h)
+    g.upload(0, src); o.upload(0, src)
+    sentinel = _rand(rng, 0, w // 2, h // 2)
+    rects = [(0, 0, w, h), (1, 0, w, h), (0, 0, w - 1, h), (3, 5, 700, 60), (517, 2, 1301, 97), (2, 0, 1299, 1), (5, 7, 521, 9)]
+    for _ in range(12):
+        x0 = int(rng.integers(0, w - 600)); y0 = int(rng.integers(0, h - 1))
+        rects.append((x0, y0, int(rng.integers(x0 + 560, w + 1)), int(rng.integers(y0 + 1, h + 1))))
+    for r in rects:
+        g.upload(1, sentinel); o.upload(1, sentinel)
+        assert g.generateNextLevel(1, r, 1) == o.generateNextLevel(1, r, 1)
+        assert np.array_equal(g.download(1), o.download(1)), r
+
+
 def test_premul_box_rounding_known_answer(b2, oracle):
     """A 2x2 quad whose green mean lands exactly on x.5 before the +0.5: ((A+B)+C)+D of singly rounded products gives
     43, a fused multiply-add anywhere in the chain (or another summation order) gives 42.  Found by the fused-chain
