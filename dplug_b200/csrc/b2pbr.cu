@@ -83,6 +83,9 @@ static int stagingReserve(uint8_t** buf, size_t* have, size_t need, cudaStream_t
     return B2_OK;
 }
 
+struct b2mip;
+static int mipUploadRows(b2mip* m, int level, int y0, int y1, const void* hostPixels, size_t hostPitch, cudaStream_t st);
+
 static int countLevels(int maxLevel, int w, int h) {  // mipmap.d:83-94
     int needed = 0;
     for (; needed <= maxLevel; ++needed) {
@@ -141,6 +144,25 @@ static int mipCreate(b2mip** out, int device, int color, int maxLevel, int w, in
     int rc = mipAllocate(m, maxLevel);
     if (rc != B2_OK) { if (m->alloc) cudaFree(m->alloc); cudaStreamDestroy(m->stream); delete m; return rc; }
     *out = m;
+    return B2_OK;
+}
+
+// whole rows [y0, y1) of a level from a host image (pixel (0,0) at hostPixels), on stream `st`
+static int mipUploadRows(b2mip* m, int level, int y0, int y1, const void* hostPixels, size_t hostPitch, cudaStream_t st) {
+    if (y1 <= y0) return B2_OK;
+    const DevLevel& L = m->levels[level];
+    uint8_t* dst = L.base + (size_t)(y0 - L.y0) * L.pitch;
+    const uint8_t* src = (const uint8_t*)hostPixels + (size_t)y0 * hostPitch;
+    const size_t rowBytes = (size_t)L.w * m->elem, rows = (size_t)(y1 - y0);
+    if (rowBytes == hostPitch && hostPitch == (size_t)L.pitch)               // gapless on both sides: one linear copy
+        CU(cudaMemcpyAsync(dst, src, rowBytes * rows, cudaMemcpyHostToDevice, st));
+    else if (rowBytes == hostPitch && rows > 1) {                             // gapless host rows: linear copy, re-pitch on the device
+        int rc = stagingReserve(&m->staging, &m->stagingBytes, rowBytes * rows, st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(m->staging, src, rowBytes * rows, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpy2DAsync(dst, (size_t)L.pitch, m->staging, rowBytes, rowBytes, rows, cudaMemcpyDeviceToDevice, st));
+    } else
+        CU(cudaMemcpy2DAsync(dst, (size_t)L.pitch, src, hostPitch, rowBytes, rows, cudaMemcpyHostToDevice, st));
     return B2_OK;
 }
 
@@ -330,19 +352,14 @@ int b2mip_upload(b2mip* m, int level, const void* host, size_t host_pitch, const
     mergeRects(rects, n, merged);
     for (const b2_box2i& r : merged) {
         const DevLevel& L = m->levels[level];
+        if (r.min_x == 0 && r.max_x == L.w) {    // whole rows
+            int rc = mipUploadRows(m, level, r.min_y, r.max_y, host, host_pitch, m->stream);
+            if (rc) return rc;
+            continue;
+        }
         uint8_t* dst = L.base + (size_t)(r.min_y - L.y0) * L.pitch + (size_t)r.min_x * m->elem;
         const uint8_t* src = (const uint8_t*)host + (size_t)r.min_y * host_pitch + (size_t)r.min_x * m->elem;
-        const size_t rowBytes = (size_t)boxW(r) * m->elem;
-        if (rowBytes == host_pitch && host_pitch == (size_t)L.pitch)               // gapless on both sides
-            CU(cudaMemcpyAsync(dst, src, rowBytes * (size_t)boxH(r), cudaMemcpyHostToDevice, m->stream));
-        else if (rowBytes == host_pitch && boxH(r) > 1) {                           // gapless host rows: linear copy, re-pitch on the device
-            const size_t bytes = rowBytes * (size_t)boxH(r);
-            int rc = stagingReserve(&m->staging, &m->stagingBytes, bytes, m->stream);
-            if (rc) return rc;
-            CU(cudaMemcpyAsync(m->staging, src, bytes, cudaMemcpyHostToDevice, m->stream));
-            CU(cudaMemcpy2DAsync(dst, (size_t)L.pitch, m->staging, rowBytes, rowBytes, (size_t)boxH(r), cudaMemcpyDeviceToDevice, m->stream));
-        } else
-            CU(cudaMemcpy2DAsync(dst, (size_t)L.pitch, src, host_pitch, rowBytes, (size_t)boxH(r), cudaMemcpyHostToDevice, m->stream));
+        CU(cudaMemcpy2DAsync(dst, (size_t)L.pitch, src, host_pitch, (size_t)boxW(r) * m->elem, (size_t)boxH(r), cudaMemcpyHostToDevice, m->stream));
     }
     return B2_OK;
 }
@@ -1282,22 +1299,20 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
                                                                      {c->material, mI, bounds[k], bounds[k + 1]},
                                                                      {c->depth, zI, bounds[k], bounds[k + 1]}};
         for (auto& u : ups) {
-            if (u.y1 <= u.y0) continue;
-            const DevLevel& L = u.m->levels[0];
-            uint8_t* dst = L.base + (size_t)(u.y0 - L.y0) * L.pitch;
-            const uint8_t* src = (const uint8_t*)u.im.pixels + (size_t)u.y0 * u.im.pitch;
-            if ((size_t)L.pitch == u.im.pitch && (size_t)W * u.m->elem == u.im.pitch)   // gapless on both sides: one linear copy
-                CU(cudaMemcpyAsync(dst, src, u.im.pitch * (size_t)(u.y1 - u.y0), cudaMemcpyHostToDevice, c->sIn));
-            else
-                CU(cudaMemcpy2DAsync(dst, (size_t)L.pitch, src, u.im.pitch, (size_t)W * u.m->elem, (size_t)(u.y1 - u.y0), cudaMemcpyHostToDevice, c->sIn));
+            int rc = mipUploadRows(u.m, 0, u.y0, u.y1, u.im.pixels, u.im.pitch, c->sIn);
+            if (rc) return rc;
         }
         CU(cudaEventRecord(c->pipeEvents[2 * k], c->sIn));
         mark(dIn, c->sIn);
     }
     if (dbg) cudaEventRecord(d1, c->sIn);
-    size_t pos = 0;
+    size_t pos = 0, dlAt = 0;
     int workPos = 0;
     int cPrev = 0;
+    if (wfb.pitch != (size_t)c->out.pitch) {   // the frame goes back through the linear device buffer (see stagingReserve)
+        int rc = stagingReserve(&c->dlStaging, &c->dlStagingBytes, ((size_t)W * 4 + 256) * (size_t)H, c->stream);
+        if (rc) return rc;
+    }
     int genD[kMaxDiffuseLevels] = {0}, genZ[kMaxDepthLevels] = {0};
     const int nD = (int)c->diffuse->levels.size(), nZ = (int)c->depth->levels.size();
     std::vector<b2_box2i> merged;
@@ -1357,10 +1372,15 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
             for (const b2_box2i& r : merged) {
                 uint8_t* hp = (uint8_t*)wfb.pixels + (size_t)r.min_y * wfb.pitch + (size_t)r.min_x * 4;
                 const uint8_t* dp = c->out.base + (size_t)(r.min_y - c->out.y0) * c->out.pitch + (size_t)r.min_x * 4;
-                if (r.min_x == 0 && r.max_x == W && wfb.pitch == (size_t)c->out.pitch && wfb.pitch == (size_t)W * 4)   // whole rows, gapless
-                    CU(cudaMemcpyAsync(hp, dp, wfb.pitch * (size_t)boxH(r), cudaMemcpyDeviceToHost, c->sOut));
-                else
-                    CU(cudaMemcpy2DAsync(hp, wfb.pitch, dp, (size_t)c->out.pitch, (size_t)boxW(r) * 4, (size_t)boxH(r), cudaMemcpyDeviceToHost, c->sOut));
+                const size_t rowBytes = (size_t)boxW(r) * 4, bytes = rowBytes * (size_t)boxH(r);
+                if (rowBytes == wfb.pitch && wfb.pitch == (size_t)c->out.pitch)                      // whole rows, gapless on both sides
+                    CU(cudaMemcpyAsync(hp, dp, bytes, cudaMemcpyDeviceToHost, c->sOut));
+                else if (rowBytes == wfb.pitch && boxH(r) > 1 && c->dlStaging && dlAt + bytes <= c->dlStagingBytes) {
+                    CU(cudaMemcpy2DAsync(c->dlStaging + dlAt, rowBytes, dp, (size_t)c->out.pitch, rowBytes, (size_t)boxH(r), cudaMemcpyDeviceToDevice, c->sOut));
+                    CU(cudaMemcpyAsync(hp, c->dlStaging + dlAt, bytes, cudaMemcpyDeviceToHost, c->sOut));
+                    dlAt += alignUp(bytes, 256);
+                } else
+                    CU(cudaMemcpy2DAsync(hp, wfb.pitch, dp, (size_t)c->out.pitch, rowBytes, (size_t)boxH(r), cudaMemcpyDeviceToHost, c->sOut));
             }
         }
         cPrev = cNew;
