@@ -22,6 +22,7 @@ void launch_box_rgba(const DevLevel& dst, const DevLevel& src, Box r, bool premu
 void launch_box_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
 void launch_cubic_rgba(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
 void launch_cubic_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
+void launch_copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t rowBytes, int rows, cudaStream_t s);
 void launch_mip_fused(bool rgba, int variant, const FusedArgs& a, int tilesY, cudaStream_t s);
 int mip_fused_tile(int n, int variant);
 void mip_fused_variants(int q0, int out[2]);
@@ -83,8 +84,17 @@ static int stagingReserve(uint8_t** buf, size_t* have, size_t need, cudaStream_t
     return B2_OK;
 }
 
+// Device-visible address of a page-locked host buffer (cudaMallocHost / cudaHostRegister), or nullptr for pageable
+// memory.  Small transfers then bypass the copy engine (k_copy2d).
+constexpr size_t kSmCopyMaxBytes = 4u << 20;
+static void* mappedHostPointer(const void* host) {
+    void* dev = nullptr;
+    if (cudaHostGetDevicePointer(&dev, const_cast<void*>(host), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return dev;
+}
+
 struct b2mip;
-static int mipUploadRows(b2mip* m, int level, int y0, int y1, const void* hostPixels, size_t hostPitch, cudaStream_t st);
+static int mipUploadRows(b2mip* m, int level, int y0, int y1, const void* hostPixels, size_t hostPitch, cudaStream_t st, bool allowSmCopy = true);
 
 static int countLevels(int maxLevel, int w, int h) {  // mipmap.d:83-94
     int needed = 0;
@@ -148,12 +158,19 @@ static int mipCreate(b2mip** out, int device, int color, int maxLevel, int w, in
 }
 
 // whole rows [y0, y1) of a level from a host image (pixel (0,0) at hostPixels), on stream `st`
-static int mipUploadRows(b2mip* m, int level, int y0, int y1, const void* hostPixels, size_t hostPitch, cudaStream_t st) {
+static int mipUploadRows(b2mip* m, int level, int y0, int y1, const void* hostPixels, size_t hostPitch, cudaStream_t st, bool allowSmCopy) {
     if (y1 <= y0) return B2_OK;
     const DevLevel& L = m->levels[level];
     uint8_t* dst = L.base + (size_t)(y0 - L.y0) * L.pitch;
     const uint8_t* src = (const uint8_t*)hostPixels + (size_t)y0 * hostPitch;
     const size_t rowBytes = (size_t)L.w * m->elem, rows = (size_t)(y1 - y0);
+    if (allowSmCopy && rowBytes * rows <= kSmCopyMaxBytes)
+        if (void* mapped = mappedHostPointer(src)) {                          // small + page-locked: the SMs read the host image in place
+            launch_copy2d(dst, (size_t)L.pitch, mapped, hostPitch, rowBytes, (int)rows, st);
+            m->launches++;
+            CU(cudaGetLastError());
+            return B2_OK;
+        }
     if (rowBytes == hostPitch && hostPitch == (size_t)L.pitch)               // gapless on both sides: one linear copy
         CU(cudaMemcpyAsync(dst, src, rowBytes * rows, cudaMemcpyHostToDevice, st));
     else if (rowBytes == hostPitch && rows > 1) {                             // gapless host rows: linear copy, re-pitch on the device
@@ -359,6 +376,13 @@ int b2mip_upload(b2mip* m, int level, const void* host, size_t host_pitch, const
         }
         uint8_t* dst = L.base + (size_t)(r.min_y - L.y0) * L.pitch + (size_t)r.min_x * m->elem;
         const uint8_t* src = (const uint8_t*)host + (size_t)r.min_y * host_pitch + (size_t)r.min_x * m->elem;
+        if ((size_t)boxW(r) * m->elem * (size_t)boxH(r) <= kSmCopyMaxBytes)
+            if (void* mapped = mappedHostPointer(src)) {
+                launch_copy2d(dst, (size_t)L.pitch, mapped, host_pitch, (size_t)boxW(r) * m->elem, boxH(r), m->stream);
+                m->launches++;
+                CU(cudaGetLastError());
+                continue;
+            }
         CU(cudaMemcpy2DAsync(dst, (size_t)L.pitch, src, host_pitch, (size_t)boxW(r) * m->elem, (size_t)boxH(r), cudaMemcpyHostToDevice, m->stream));
     }
     return B2_OK;
@@ -501,7 +525,7 @@ int b2_dirty_rects_pull_all(b2_dirty_rects* d, b2_box2i* out, int cap) {
 int b2_have_no_overlap(const b2_box2i* boxes, int n) { return (n <= 0 || (boxes && haveNoOverlap(boxes, n))) ? 1 : 0; }
 
 int b2_host_register(void* ptr, size_t bytes) {
-    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
     return B2_OK;
 }
 int b2_host_unregister(void* ptr) {
@@ -1171,6 +1195,13 @@ int b2pbr_download(b2pbr* c, void* host, size_t host_pitch, const b2_box2i* rect
         uint8_t* hp = (uint8_t*)host + (size_t)r.min_y * host_pitch + (size_t)r.min_x * 4;
         const uint8_t* dp = c->out.base + (size_t)(r.min_y - c->out.y0) * c->out.pitch + (size_t)r.min_x * 4;
         const size_t rowBytes = (size_t)boxW(r) * 4, bytes = rowBytes * (size_t)boxH(r);
+        if (bytes <= kSmCopyMaxBytes)
+            if (void* mapped = mappedHostPointer(hp)) {                            // small + page-locked: the SMs write the host image in place
+                launch_copy2d(mapped, host_pitch, dp, (size_t)c->out.pitch, rowBytes, boxH(r), c->stream);
+                c->launches++;
+                CU(cudaGetLastError());
+                continue;
+            }
         if (rowBytes == host_pitch && host_pitch == (size_t)c->out.pitch)          // gapless on both sides
             CU(cudaMemcpyAsync(hp, dp, bytes, cudaMemcpyDeviceToHost, c->stream));
         else if (rowBytes == host_pitch && boxH(r) > 1 && stagedAt + bytes <= ((size_t)c->W * 4) * (size_t)c->H) {
@@ -1299,7 +1330,7 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
                                                                      {c->material, mI, bounds[k], bounds[k + 1]},
                                                                      {c->depth, zI, bounds[k], bounds[k + 1]}};
         for (auto& u : ups) {
-            int rc = mipUploadRows(u.m, 0, u.y0, u.y1, u.im.pixels, u.im.pitch, c->sIn);
+            int rc = mipUploadRows(u.m, 0, u.y0, u.y1, u.im.pixels, u.im.pitch, c->sIn, false);   // large frames: the copy engine, next to the kernels
             if (rc) return rc;
         }
         CU(cudaEventRecord(c->pipeEvents[2 * k], c->sIn));

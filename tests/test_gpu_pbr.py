@@ -274,6 +274,40 @@ def test_host_call_full_frame_pipelined(b2, oracle):
         _compare(wfb[band[1]:band[3]], np.array(ref.output())[band[1]:band[3]], "pipelined %s" % (band,))
 
 
+def test_page_locked_host_images(b2):
+    """Page-locked host images take other transfer paths than pageable ones (small: the SMs copy through the mapped
+    addresses; pitched: one linear PCIe copy + a device re-pitch): same bytes either way, for the whole-frame host call,
+    for dirty rectangles and for Mipmap.upload / download."""
+    import ctypes as C
+    from dplug_b200 import _lib
+    l = _lib.lib()
+    W, H = 324, 200          # 324 * 2 bytes is not a multiple of 16: the L16 copy falls back to narrower vectors
+    d, m, z = synth.frame(W, H)
+    pin = [d.copy(), m.copy(), z.copy(), np.zeros((H, W, 4), np.uint8)]
+    for b in pin:
+        assert l.b2_host_register(b.ctypes.data_as(C.c_void_p), b.nbytes) == 0
+    try:
+        a = b2.PBRCompositor(0); a.resizeBuffers(W, H); a.setSkybox(synth.skybox(128, 96))
+        p = b2.PBRCompositor(0); p.resizeBuffers(W, H); p.setSkybox(synth.skybox(128, 96))
+        tiles = b2.tileAreas([(0, 0, W, H)], 64, 64)
+        want = np.zeros((H, W, 4), np.uint8)
+        a.compositeTile(want, tiles, d, m, z, updateRects=[(0, 0, W, H)])
+        p.compositeTile(pin[3], tiles, pin[0], pin[1], pin[2], updateRects=[(0, 0, W, H)])
+        assert np.array_equal(pin[3], want)
+        d2, m2, z2 = synth.frame(W, H, synth.SEED + 5)
+        r = [(37, 21, 201, 150)]
+        for src, dst in ((d2, pin[0]), (m2, pin[1]), (z2, pin[2])):
+            dst[...] = src
+        a.compositeTile(want, b2.tileAreas(r, 64, 64), d2, m2, z2, updateRects=r)
+        p.compositeTile(pin[3], b2.tileAreas(r, 64, 64), pin[0], pin[1], pin[2], updateRects=r)
+        assert np.array_equal(pin[3], want)
+        for which in (0, 1, 2):
+            assert np.array_equal(a.map(which).download(0), p.map(which).download(0)), which
+    finally:
+        for b in pin:
+            l.b2_host_unregister(b.ctypes.data_as(C.c_void_p))
+
+
 def test_cuda_graph_replay(b2):
     """A frame recorded with graphBegin/graphEnd replays to the same bytes, also after the inputs changed."""
     W, H = 512, 384
