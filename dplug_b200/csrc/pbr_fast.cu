@@ -50,6 +50,10 @@ struct RowSetup {            // vertical sampler set-up of one row; texel rows a
     int ib4, ib5;            // bicubic interval (floor(y_s) + 1) of diffuse levels 4 and 5
     float wy4[4], wy5[4];    // Catmull-Rom weights of the four rows
     float ey, ey2;           // toEye.y = j / H - 0.5 and its square (legacypbr.d:756, 914), exact
+    // which rolling rows change at this row (compared with the row above; everything on a strip's first row):
+    // bits 0-2 bilinear levels 1-3, bit 3 depth level 4, bits 4-5 / 6-7 bicubic levels 4 / 5 (1 = slide by one, 2 = reload)
+    int refresh;
+    int pad[3];
 };
 static_assert(sizeof(RowSetup) % 16 == 0, "RowSetup is read with 128-bit shared loads");
 
@@ -230,6 +234,22 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         cubCoord(5, j, rs.ib5, t); catmullRomWeights(t, rs.wy5);
         rs.ey = __fsub_rn(__fmul_rn((float)j, P.invH), 0.5f);
         rs.ey2 = __fmul_rn(rs.ey, rs.ey);
+        int refresh = 0xaf;                        // first row of the strip: everything is (re)loaded
+        if (lane > 0) {
+            refresh = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                Lin y = linCoord(k + 1, j - 1, k < 3 ? P.diffuse[k + 1].h : P.depth[4].h);
+                if (y.i0 - oy[k] != rs.iy[k] || y.i1 - oy[k] != rs.iy1[k]) refresh |= 1 << k;
+            }
+            int ibp; float tp;
+            cubCoord(4, j - 1, ibp, tp);
+            if (rs.ib4 != ibp) refresh |= (rs.ib4 == ibp + 1 ? 1 : 2) << 4;
+            cubCoord(5, j - 1, ibp, tp);
+            if (rs.ib5 != ibp) refresh |= (rs.ib5 == ibp + 1 ? 1 : 2) << 6;
+        }
+        rs.refresh = refresh;
+        rs.pad[0] = rs.pad[1] = rs.pad[2] = 0;
         S.rows[lane] = rs;
     }
     __syncwarp();
@@ -276,10 +296,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
     };
 
     // rolling state: bilinear levels keep (row A, row B - row A); bicubic levels keep their four rows
-    int rowA1 = -1, rowB1 = -1, rowA2 = -1, rowB2 = -1, rowA3 = -1, rowB3 = -1, rowA4 = -1, rowB4 = -1;
     F3 a1{0, 0, 0}, d1 = a1, a2 = a1, d2 = a1, a3 = a1, d3 = a1;
     float za1 = 0, zd1 = 0, za2 = 0, zd2 = 0, za3 = 0, zd3 = 0, za4 = 0, zd4 = 0;
-    int base4 = (int)0x80000000, base5 = base4;
     F3 p4[4], p5[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) p4[k] = p5[k] = a1;
@@ -322,15 +340,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         // rolling rows of levels 1..3: the diffuse and depth pyramids share the texel rows, one warp-uniform test
         // per level refreshes both (the rows are recomputed from the staged windows, so the result does not depend
         // on where the strip starts)
-        if (rs.iy[0] != rowA1 || rs.iy1[0] != rowB1) {
+        const int refresh = rs.refresh;
+        if (refresh & 1) {
             if (needMipsD) { F3 na = hrow1(rs.iy[0]), nb = hrow1(rs.iy1[0]); a1 = na; d1 = nb - na; }
             if (needMipsZ) { float na = zrow1(rs.iy[0]), nb = zrow1(rs.iy1[0]); za1 = na; zd1 = nb - na; }
         }
-        if (rs.iy[1] != rowA2 || rs.iy1[1] != rowB2) {
+        if (refresh & 2) {
             if (needMipsD) { F3 na = hrow2(rs.iy[1]), nb = hrow2(rs.iy1[1]); a2 = na; d2 = nb - na; }
             if (needMipsZ) { float na = zrow2(rs.iy[1]), nb = zrow2(rs.iy1[1]); za2 = na; zd2 = nb - na; }
         }
-        if (rs.iy[2] != rowA3 || rs.iy1[2] != rowB3) {
+        if (refresh & 4) {
             if (needMipsD) { F3 na = hrow3(rs.iy[2]), nb = hrow3(rs.iy1[2]); a3 = na; d3 = nb - na; }
             if (needMipsZ) { float na = zrow3(rs.iy[2]), nb = zrow3(rs.iy1[2]); za3 = na; zd3 = nb - na; }
         }
@@ -384,7 +403,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
 
         // ---- PassAmbientOcclusion (legacypbr.d:400-444): depth levels 1..4, bilinear
         if (needMipsZ) {
-            if (rs.iy[3] != rowA4 || rs.iy1[3] != rowB4) {
+            if (refresh & 8) {
                 float na = zrow4(rs.iy[3]), nb = zrow4(rs.iy1[3]);
                 za4 = na; zd4 = nb - na;
             }
@@ -504,21 +523,19 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         // ---- PassEmissiveContribution (legacypbr.d:948-1007, non-legacy branch): diffuse levels 1..3 bilinear,
         // 4 and 5 bicubic
         if (needMipsD) {
-            if (rs.ib4 != base4) {
-                if (rs.ib4 == base4 + 1) { p4[0] = p4[1]; p4[1] = p4[2]; p4[2] = p4[3]; p4[3] = crow4(rs.ib4, 3); }
+            if (refresh & 0x30) {
+                if (refresh & 0x10) { p4[0] = p4[1]; p4[1] = p4[2]; p4[2] = p4[3]; p4[3] = crow4(rs.ib4, 3); }
                 else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) p4[k] = crow4(rs.ib4, k);
                 }
-                base4 = rs.ib4;
             }
-            if (rs.ib5 != base5) {
-                if (rs.ib5 == base5 + 1) { p5[0] = p5[1]; p5[1] = p5[2]; p5[2] = p5[3]; p5[3] = crow5(rs.ib5, 3); }
+            if (refresh & 0xc0) {
+                if (refresh & 0x40) { p5[0] = p5[1]; p5[1] = p5[2]; p5[2] = p5[3]; p5[3] = crow5(rs.ib5, 3); }
                 else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) p5[k] = crow5(rs.ib5, k);
                 }
-                base5 = rs.ib5;
             }
             F3 s = fma3(rs.fy[0], d1, a1) + fma3(rs.fy[1], d2, a2) + fma3(rs.fy[2], d3, a3);
             F3 c4 = fma3(rs.wy4[3], p4[3], fma3(rs.wy4[2], p4[2], fma3(rs.wy4[1], p4[1], p4[0] * rs.wy4[0])));
@@ -533,9 +550,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
             accum.y = fmaf(c5.y, k5, fmaf(s.y, AMT, accum.y));
             accum.z = fmaf(c5.z, k5, fmaf(s.z, AMT, accum.z));
         }
-        // the depth and diffuse pyramids share the row bookkeeping of levels 1..3
-        rowA1 = rs.iy[0]; rowB1 = rs.iy1[0]; rowA2 = rs.iy[1]; rowB2 = rs.iy1[1];
-        rowA3 = rs.iy[2]; rowB3 = rs.iy1[2]; rowA4 = rs.iy[3]; rowB4 = rs.iy1[3];
 
         // ---- PassClampAndConvertTo8bit (legacypbr.d:1057-1107, non-legacy branch)
         if ((mask & 0x80u) && active) {
