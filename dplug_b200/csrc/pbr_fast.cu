@@ -62,6 +62,8 @@ struct alignas(16) WarpSmem {
     uint16_t depth[TILE_ROWS][TILE_COLS];   // raw L16; converted on use (keeps 4 CTAs / 16 warps per SM resident)
     uint32_t d1[W1][W1], d2[W2][W2], d3[W3][W3], d4[WC4][WC4], d5[WC5][WC5];
     uint16_t z1[W1][W1], z2[W2][W2], z3[W3][W3], z4[WZ4][WZ4];
+    int org[12];   // window origins ox1, oy1, ox2, oy2, ox3, oy3, oxz4, oyz4, ox4, oy4, ox5, oy5 (re-read by the refresh blocks)
+    int pad[4];
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "per-warp shared block keeps 16-byte alignment");
 
@@ -188,6 +190,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
     cubCoord(5, box.minx, ibx, tt); cubCoord(5, box.miny, iby, tt);
     const int ox5 = max(0, min(ibx - 2, P.diffuse[5].w - 1)), oy5 = max(0, min(iby - 2, P.diffuse[5].h - 1));
 
+    if (lane == 0) {
+        const int o[12] = {ox1, oy1, ox2, oy2, ox3, oy3, oxz4, oyz4, ox4, oy4, ox5, oy5};
+#pragma unroll
+        for (int k = 0; k < 12; ++k) S.org[k] = o[k];
+    }
     stageWindow<uint32_t, W1, W1>(S.d1, P.diffuse[1], ox1, oy1, lane);
     stageWindow<uint16_t, W1, W1>(S.z1, P.depth[1], ox1, oy1, lane);
     stageWindow<uint32_t, W2, W2>(S.d2, P.diffuse[2], ox2, oy2, lane);
@@ -254,45 +261,50 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
     }
     __syncwarp();
 
-    // ---------------------------------------------------------------- per-column set-up (window-relative)
-    const Lin c1 = linCoord(1, ic, P.diffuse[1].w), c2 = linCoord(2, ic, P.diffuse[2].w), c3 = linCoord(3, ic, P.diffuse[3].w);
-    const Lin cz4 = linCoord(4, ic, P.depth[4].w);
-    const int x1a = c1.i0 - ox1, x1b = c1.i1 - ox1, x2a = c2.i0 - ox2, x2b = c2.i1 - ox2, x3a = c3.i0 - ox3, x3b = c3.i1 - ox3;
-    const int xz4a = cz4.i0 - oxz4, xz4b = cz4.i1 - oxz4;
-    int xc4[4], xc5[4];
-    float wx4[4], wx5[4];
-    {
-        int ib; float t;
-        cubCoord(4, ic, ib, t); catmullRomWeights(t, wx4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) xc4[k] = max(0, min(ib - 2 + k, P.diffuse[4].w - 1)) - ox4;
-        cubCoord(5, ic, ib, t); catmullRomWeights(t, wx5);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) xc5[k] = max(0, min(ib - 2 + k, P.diffuse[5].w - 1)) - ox5;
-    }
-    const int h4 = P.diffuse[4].h, h5 = P.diffuse[5].h;
-
-    // horizontal interpolation of one staged texel row for this lane's column
-    auto hrow1 = [&](int r) { F3 A = rgbOf(S.d1[r][x1a]), B = rgbOf(S.d1[r][x1b]); return fma3(c1.f, B - A, A); };
-    auto hrow2 = [&](int r) { F3 A = rgbOf(S.d2[r][x2a]), B = rgbOf(S.d2[r][x2b]); return fma3(c2.f, B - A, A); };
-    auto hrow3 = [&](int r) { F3 A = rgbOf(S.d3[r][x3a]), B = rgbOf(S.d3[r][x3b]); return fma3(c3.f, B - A, A); };
-    auto zrow1 = [&](int r) { float A = u16ToFloat(S.z1[r][x1a]), B = u16ToFloat(S.z1[r][x1b]); return fmaf(c1.f, B - A, A); };
-    auto zrow2 = [&](int r) { float A = u16ToFloat(S.z2[r][x2a]), B = u16ToFloat(S.z2[r][x2b]); return fmaf(c2.f, B - A, A); };
-    auto zrow3 = [&](int r) { float A = u16ToFloat(S.z3[r][x3a]), B = u16ToFloat(S.z3[r][x3b]); return fmaf(c3.f, B - A, A); };
-    auto zrow4 = [&](int r) { float A = u16ToFloat(S.z4[r][xz4a]), B = u16ToFloat(S.z4[r][xz4b]); return fmaf(cz4.f, B - A, A); };
-    auto crow4 = [&](int ib, int k) {
-        const int r = max(0, min(ib - 2 + k, h4 - 1)) - oy4;
-        F3 v = rgbOf(S.d4[r][xc4[0]]) * wx4[0];
-        v = fma3(wx4[1], rgbOf(S.d4[r][xc4[1]]), v);
-        v = fma3(wx4[2], rgbOf(S.d4[r][xc4[2]]), v);
-        return fma3(wx4[3], rgbOf(S.d4[r][xc4[3]]), v);
+    // ---------------------------------------------------------------- per-column sampler set-up
+    // The horizontal set-up of a level (texel columns, fraction, Catmull-Rom weights) is needed only when one of its
+    // rolling rows is refreshed — every 2^level rows.  It is RECOMPUTED there from the lane's column (a dozen integer
+    // operations) instead of living in ~32 registers for the whole strip: the kernel is register-bound (every register
+    // saved is occupancy or a spill avoided), and the refresh blocks are off the per-pixel path.  `opaque` keeps the
+    // compiler from hoisting the recomputation back out of the row loop.
+    auto opaque = [](int v) { asm volatile("" : "+r"(v)); return v; };
+    const volatile int* org = S.org;
+    // bilinear level l (1..3 diffuse + depth, 4 depth only): refresh (a, b - a) of the colour and / or the depth row pair
+    auto refreshLin = [&](int l, int lw, auto& win, auto& zwin, int oIdx, int rA, int rB, bool doD, bool doZ, F3& a, F3& d, float& za, float& zd) {
+        const Lin c = linCoord(l, opaque(ic), lw);
+        const int ox = org[oIdx], xa = c.i0 - ox, xb = c.i1 - ox;
+        if (doD) {
+            const F3 A0 = rgbOf(win[rA][xa]), B0 = rgbOf(win[rA][xb]), A1 = rgbOf(win[rB][xa]), B1 = rgbOf(win[rB][xb]);
+            const F3 na = fma3(c.f, B0 - A0, A0), nb = fma3(c.f, B1 - A1, A1);
+            a = na; d = nb - na;
+        }
+        if (doZ) {
+            const float A0 = u16ToFloat(zwin[rA][xa]), B0 = u16ToFloat(zwin[rA][xb]), A1 = u16ToFloat(zwin[rB][xa]), B1 = u16ToFloat(zwin[rB][xb]);
+            const float na = fmaf(c.f, B0 - A0, A0), nb = fmaf(c.f, B1 - A1, A1);
+            za = na; zd = nb - na;
+        }
     };
-    auto crow5 = [&](int ib, int k) {
-        const int r = max(0, min(ib - 2 + k, h5 - 1)) - oy5;
-        F3 v = rgbOf(S.d5[r][xc5[0]]) * wx5[0];
-        v = fma3(wx5[1], rgbOf(S.d5[r][xc5[1]]), v);
-        v = fma3(wx5[2], rgbOf(S.d5[r][xc5[2]]), v);
-        return fma3(wx5[3], rgbOf(S.d5[r][xc5[3]]), v);
+    // bicubic level (4 or 5): slide the four horizontally interpolated rows by one, or reload all of them
+    auto refreshCub = [&](int l, const DevLevel& L, auto& win, int oIdx, int ib, bool slide, F3 (&p)[4]) {
+        int ibx; float t, w[4];
+        cubCoord(l, opaque(ic), ibx, t);
+        catmullRomWeights(t, w);
+        const int ox = org[oIdx], oy = org[oIdx + 1];
+        int xc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xc[k] = max(0, min(ibx - 2 + k, L.w - 1)) - ox;
+        auto row = [&](int k) {
+            const int r = max(0, min(ib - 2 + k, L.h - 1)) - oy;
+            F3 v = rgbOf(win[r][xc[0]]) * w[0];
+            v = fma3(w[1], rgbOf(win[r][xc[1]]), v);
+            v = fma3(w[2], rgbOf(win[r][xc[2]]), v);
+            return fma3(w[3], rgbOf(win[r][xc[3]]), v);
+        };
+        if (slide) { p[0] = p[1]; p[1] = p[2]; p[2] = p[3]; p[3] = row(3); }
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p[k] = row(k);
+        }
     };
 
     // rolling state: bilinear levels keep (row A, row B - row A); bicubic levels keep their four rows
@@ -341,18 +353,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         // per level refreshes both (the rows are recomputed from the staged windows, so the result does not depend
         // on where the strip starts)
         const int refresh = rs.refresh;
-        if (refresh & 1) {
-            if (needMipsD) { F3 na = hrow1(rs.iy[0]), nb = hrow1(rs.iy1[0]); a1 = na; d1 = nb - na; }
-            if (needMipsZ) { float na = zrow1(rs.iy[0]), nb = zrow1(rs.iy1[0]); za1 = na; zd1 = nb - na; }
-        }
-        if (refresh & 2) {
-            if (needMipsD) { F3 na = hrow2(rs.iy[1]), nb = hrow2(rs.iy1[1]); a2 = na; d2 = nb - na; }
-            if (needMipsZ) { float na = zrow2(rs.iy[1]), nb = zrow2(rs.iy1[1]); za2 = na; zd2 = nb - na; }
-        }
-        if (refresh & 4) {
-            if (needMipsD) { F3 na = hrow3(rs.iy[2]), nb = hrow3(rs.iy1[2]); a3 = na; d3 = nb - na; }
-            if (needMipsZ) { float na = zrow3(rs.iy[2]), nb = zrow3(rs.iy1[2]); za3 = na; zd3 = nb - na; }
-        }
+        if (refresh & 1) refreshLin(1, P.diffuse[1].w, S.d1, S.z1, 0, rs.iy[0], rs.iy1[0], needMipsD, needMipsZ, a1, d1, za1, zd1);
+        if (refresh & 2) refreshLin(2, P.diffuse[2].w, S.d2, S.z2, 2, rs.iy[1], rs.iy1[1], needMipsD, needMipsZ, a2, d2, za2, zd2);
+        if (refresh & 4) refreshLin(3, P.diffuse[3].w, S.d3, S.z3, 4, rs.iy[2], rs.iy1[2], needMipsD, needMipsZ, a3, d3, za3, zd3);
 
         const F3 base = rgbOf(diffusePx) * div255;
         const float rough = byteToFloat(materialPx, 0) * div255;
@@ -403,10 +406,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
 
         // ---- PassAmbientOcclusion (legacypbr.d:400-444): depth levels 1..4, bilinear
         if (needMipsZ) {
-            if (refresh & 8) {
-                float na = zrow4(rs.iy[3]), nb = zrow4(rs.iy1[3]);
-                za4 = na; zd4 = nb - na;
-            }
+            if (refresh & 8) { F3 unusedA, unusedD; refreshLin(4, P.depth[4].w, S.z4, S.z4, 6, rs.iy[3], rs.iy1[3], false, true, unusedA, unusedD, za4, zd4); }
             float s = fmaf(rs.fy[0], zd1, za1) + fmaf(rs.fy[1], zd2, za2) + fmaf(rs.fy[2], zd3, za3) + fmaf(rs.fy[3], zd4, za4);
             float diff = fmaf(s, -0.25f, zc);
             float cavity = fmaSat(diff, 1.0f / 23040, 1.0f);
@@ -523,20 +523,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         // ---- PassEmissiveContribution (legacypbr.d:948-1007, non-legacy branch): diffuse levels 1..3 bilinear,
         // 4 and 5 bicubic
         if (needMipsD) {
-            if (refresh & 0x30) {
-                if (refresh & 0x10) { p4[0] = p4[1]; p4[1] = p4[2]; p4[2] = p4[3]; p4[3] = crow4(rs.ib4, 3); }
-                else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) p4[k] = crow4(rs.ib4, k);
-                }
-            }
-            if (refresh & 0xc0) {
-                if (refresh & 0x40) { p5[0] = p5[1]; p5[1] = p5[2]; p5[2] = p5[3]; p5[3] = crow5(rs.ib5, 3); }
-                else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) p5[k] = crow5(rs.ib5, k);
-                }
-            }
+            if (refresh & 0x30) refreshCub(4, P.diffuse[4], S.d4, 8, rs.ib4, (refresh & 0x10) != 0, p4);
+            if (refresh & 0xc0) refreshCub(5, P.diffuse[5], S.d5, 10, rs.ib5, (refresh & 0x40) != 0, p5);
             F3 s = fma3(rs.fy[0], d1, a1) + fma3(rs.fy[1], d2, a2) + fma3(rs.fy[2], d3, a3);
             F3 c4 = fma3(rs.wy4[3], p4[3], fma3(rs.wy4[2], p4[2], fma3(rs.wy4[1], p4[1], p4[0] * rs.wy4[0])));
             F3 c5 = fma3(rs.wy5[3], p5[3], fma3(rs.wy5[2], p5[2], fma3(rs.wy5[1], p5[1], p5[0] * rs.wy5[0])));
