@@ -404,6 +404,49 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         const float zc = u16ToFloat(trow[0]);
         F3 T{0, 0, 0};   // light arriving per channel; every pass but the emissive one is base colour x light
 
+        // toEye (legacypbr.d:756-757, 914-915): exact operand for RSQRTSS, shared by specular and skybox
+        float ex = eyeX, ey = 0, ez = 1.0f;
+        if (mask & 0x30u) {
+            ey = rs.ey;
+            float len2 = __fadd_rn(__fadd_rn(eyeX2, rs.ey2), 1.0f);
+            float inv = rsqrtssPos(P.rsqrtTab, len2);
+            ex = __fmul_rn(eyeX, inv); ey = __fmul_rn(ey, inv); ez = inv;  // 1.0f * inv
+        }
+
+        // ---- PassSkyboxReflections (legacypbr.d:872-930), first half: the eight texel loads of the trilinear sample are the
+        // only dependent global loads of a row (coordinates come from the normal), so they are issued HERE, before the
+        // occlusion / shadow / directional / specular arithmetic, which then runs in their shadow; the blend follows
+        // after the specular pass, where the reference adds the sky term (same order of additions into T)
+        const bool doSky = HAS_SKY && (mask & 0x20u);
+        uint32_t ta = 0, tb = 0, tc = 0, td = 0, ua = 0, ub = 0, uc = 0, ud = 0;
+        float sfx = 0, sfy = 0, s2fx = 0, s2fy = 0, fl = 0;
+        if (doSky) {
+            float lod = variance * P.skyPixels;
+            lod = fmaf(0.5f, fastlog2(fmaf(lod, 0.00001f, 1.0f)), (6.0f / 255.0f) * (float)roughByte);
+            float sum = 2.0f * fmaf(ez, nzc, fmaf(ey, ny, ex * nx));  // _mm_reflectnormal_ps, ransac.d:31-36
+            float rx = fmaf(-sum, nx, ex), ry = fmaf(-sum, ny, ey);
+            float skyx = fmaf(fmaf(rx, -0.5f, 0.5f), P.skyFX, 0.5f);
+            float skyy = fmaf(fmaf(ry, 0.5f, 0.5f), P.skyFY, 0.5f);
+            int il = __float2int_rz(lod);               // linearMipmapSample, mipmap.d:149-160
+            fl = lod - (float)il;
+            const int level = max(0, min(il, P.nSky - 1));
+            const DevLevel& L = P.sky[level];
+            const Bilin s = bilinSetup(levelScale(level), skyx, skyy, L.w, L.h);
+            const uint32_t* r0 = rowPtr<uint32_t>(L, s.iy);
+            const uint32_t* r1 = rowPtr<uint32_t>(L, s.iy1);
+            ta = __ldg(r0 + s.ix); tb = __ldg(r0 + s.ix1); tc = __ldg(r1 + s.ix); td = __ldg(r1 + s.ix1);
+            sfx = s.fx; sfy = s.fy;
+            if (fl != 0.f) {  // second level of the trilinear blend
+                const int level2 = max(0, min(il + 1, P.nSky - 1));
+                const DevLevel& L2 = P.sky[level2];
+                const Bilin s2 = bilinSetup(levelScale(level2), skyx, skyy, L2.w, L2.h);
+                const uint32_t* q0 = rowPtr<uint32_t>(L2, s2.iy);
+                const uint32_t* q1 = rowPtr<uint32_t>(L2, s2.iy1);
+                ua = __ldg(q0 + s2.ix); ub = __ldg(q0 + s2.ix1); uc = __ldg(q1 + s2.ix); ud = __ldg(q1 + s2.ix1);
+                s2fx = s2.fx; s2fy = s2.fy;
+            }
+        }
+
         // ---- PassAmbientOcclusion (legacypbr.d:400-444): depth levels 1..4, bilinear
         if (needMipsZ) {
             if (refresh & 8) { F3 unusedA, unusedD; refreshLin(4, P.depth[4].w, S.z4, S.z4, 6, rs.iy[3], rs.iy1[3], false, true, unusedA, unusedD, za4, zd4); }
@@ -445,15 +488,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
             T.z = fmaf(P.light2Col[2], f, T.z);
         }
 
-        // toEye (legacypbr.d:756-757, 914-915): exact operand for RSQRTSS, shared by specular and skybox
-        float ex = eyeX, ey = 0, ez = 1.0f;
-        if (mask & 0x30u) {
-            ey = rs.ey;
-            float len2 = __fadd_rn(__fadd_rn(eyeX2, rs.ey2), 1.0f);
-            float inv = rsqrtssPos(P.rsqrtTab, len2);
-            ex = __fmul_rn(eyeX, inv); ey = __fmul_rn(ey, inv); ez = inv;  // 1.0f * inv
-        }
-
         // ---- PassSpecularLight (legacypbr.d:720-813)
         if (mask & 0x10u) {
             float hx = __fsub_rn(ex, -P.light3Dir[0]), hy = __fsub_rn(ey, -P.light3Dir[1]), hz = __fsub_rn(ez, -P.light3Dir[2]);
@@ -473,45 +507,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
             T.z = fmaf(P.light3Col[2], k, T.z);
         }
 
-        // ---- PassSkyboxReflections (legacypbr.d:872-930)
-        if (HAS_SKY && (mask & 0x20u)) {
-            float lod = variance * P.skyPixels;
-            lod = fmaf(0.5f, fastlog2(fmaf(lod, 0.00001f, 1.0f)), (6.0f / 255.0f) * (float)roughByte);
-            float sum = 2.0f * fmaf(ez, nzc, fmaf(ey, ny, ex * nx));  // _mm_reflectnormal_ps, ransac.d:31-36
-            float rx = fmaf(-sum, nx, ex), ry = fmaf(-sum, ny, ey);
-            float skyx = fmaf(fmaf(rx, -0.5f, 0.5f), P.skyFX, 0.5f);
-            float skyy = fmaf(fmaf(ry, 0.5f, 0.5f), P.skyFY, 0.5f);
-            int il = __float2int_rz(lod);               // linearMipmapSample, mipmap.d:149-160
-            float fl = lod - (float)il;
-            F3 sky;
-            {
-                const int level = max(0, min(il, P.nSky - 1));
-                const DevLevel& L = P.sky[level];
-                Bilin s = bilinSetup(levelScale(level), skyx, skyy, L.w, L.h);
-                const uint32_t* r0 = rowPtr<uint32_t>(L, s.iy);
-                const uint32_t* r1 = rowPtr<uint32_t>(L, s.iy1);
-                uint32_t ta = __ldg(r0 + s.ix), tb = __ldg(r0 + s.ix1), tc = __ldg(r1 + s.ix), td = __ldg(r1 + s.ix1);
-                uint32_t ua = 0, ub = 0, uc = 0, ud = 0;
-                Bilin s2 = s;
-                if (fl != 0.f) {  // second level of the trilinear blend: issue its loads before using the first
-                    const int level2 = max(0, min(il + 1, P.nSky - 1));
-                    const DevLevel& L2 = P.sky[level2];
-                    s2 = bilinSetup(levelScale(level2), skyx, skyy, L2.w, L2.h);
-                    const uint32_t* q0 = rowPtr<uint32_t>(L2, s2.iy);
-                    const uint32_t* q1 = rowPtr<uint32_t>(L2, s2.iy1);
-                    ua = __ldg(q0 + s2.ix); ub = __ldg(q0 + s2.ix1); uc = __ldg(q1 + s2.ix); ud = __ldg(q1 + s2.ix1);
-                }
-                F3 A = rgbBiased(ta), B = rgbBiased(tb), C = rgbBiased(tc), D = rgbBiased(td);
-                F3 up = fma3(s.fx, B - A, A), down = fma3(s.fx, D - C, C);
-                sky = fma3(s.fy, down - up, up);
-                if (fl != 0.f) {
-                    F3 A2 = rgbBiased(ua), B2 = rgbBiased(ub), C2 = rgbBiased(uc), D2 = rgbBiased(ud);
-                    F3 up2 = fma3(s2.fx, B2 - A2, A2), down2 = fma3(s2.fx, D2 - C2, C2);
-                    F3 sky1 = fma3(s2.fy, down2 - up2, up2);
-                    sky = fma3(fl, sky1 - sky, sky);
-                }
-                sky = F3{sky.x - 32768.0f, sky.y - 32768.0f, sky.z - 32768.0f};
+        // ---- PassSkyboxReflections, second half: blend the texels loaded above
+        if (doSky) {
+            F3 A = rgbBiased(ta), B = rgbBiased(tb), C = rgbBiased(tc), D = rgbBiased(td);
+            F3 up = fma3(sfx, B - A, A), down = fma3(sfx, D - C, C);
+            F3 sky = fma3(sfy, down - up, up);
+            if (fl != 0.f) {
+                F3 A2 = rgbBiased(ua), B2 = rgbBiased(ub), C2 = rgbBiased(uc), D2 = rgbBiased(ud);
+                F3 up2 = fma3(s2fx, B2 - A2, A2), down2 = fma3(s2fx, D2 - C2, C2);
+                F3 sky1 = fma3(s2fy, down2 - up2, up2);
+                sky = fma3(fl, sky1 - sky, sky);
             }
+            sky = F3{sky.x - 32768.0f, sky.y - 32768.0f, sky.z - 32768.0f};
             float k = metal * (P.skyAmount * div255);
             T.x = fmaf(sky.x, k, T.x);
             T.y = fmaf(sky.y, k, T.y);
