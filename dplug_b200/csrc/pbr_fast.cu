@@ -61,7 +61,7 @@ struct alignas(16) WarpSmem {
     RowSetup rows[STRIP_ROWS];
     uint16_t depth[TILE_ROWS][TILE_COLS];   // raw L16; converted on use (keeps 4 CTAs / 16 warps per SM resident)
     uint32_t d1[W1][W1], d2[W2][W2], d3[W3][W3], d4[WC4][WC4], d5[WC5][WC5];
-    uint16_t z1[W1][W1], z2[W2][W2], z3[W3][W3], z4[WZ4][WZ4];
+    float z1[W1][W1], z2[W2][W2], z3[W3][W3], z4[WZ4][WZ4];   // depth levels 1..4, converted once when staged
     int org[12];   // window origins ox1, oy1, ox2, oy2, ox3, oy3, oxz4, oyz4, ox4, oy4, ox5, oy5 (re-read by the refresh blocks)
     int pad[4];
 };
@@ -147,13 +147,15 @@ __device__ __forceinline__ void cubCoord(int l, int p, int& ib, float& t) {
 }
 
 // copies the window [y0, y0 + WH) x [x0, x0 + WW) of a level into shared memory, clamped to the level
-template <typename T, int WW, int WH>
-__device__ __forceinline__ void stageWindow(T (*dst)[WW], const DevLevel& L, int x0, int y0, int lane) {
+template <typename T, int WW, int WH, typename D>
+__device__ __forceinline__ void stageWindow(D (*dst)[WW], const DevLevel& L, int x0, int y0, int lane) {
 #pragma unroll
     for (int idx = lane; idx < WW * WH; idx += 32) {
         const int r = idx / WW, c = idx - r * WW;
         const int gy = max(0, min(y0 + r, L.h - 1)), gx = max(0, min(x0 + c, L.w - 1));
-        dst[r][c] = __ldg(rowPtr<T>(L, gy) + gx);
+        const T v = __ldg(rowPtr<T>(L, gy) + gx);
+        if (sizeof(D) == sizeof(T)) dst[r][c] = (D)v;
+        else dst[r][c] = (D)u16ToFloat((uint32_t)v);   // L16 windows are kept as floats (exact)
     }
 }
 
@@ -215,14 +217,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         const int gx = cx0 + c;
         const bool pairOk = gx >= 0 && gx + 1 < W;
         const int gxa = max(0, min(gx, W - 1)), gxb = max(0, min(gx + 1, W - 1));
+        // two loops rather than a per-row choice (which the compiler turns into BOTH loads, predicated): the clamped
+        // texel-by-texel path is taken only by the lanes hanging over the left / right image edge
+        if (pairOk) {
 #pragma unroll 4
-        for (int r = 0; r < nRows; ++r) {
-            const int gy = max(0, min(ry0 + r, H - 1));
-            const uint16_t* src = rowPtr<uint16_t>(D0, gy);
-            uint32_t v;
-            if (pairOk) v = __ldg(reinterpret_cast<const uint32_t*>(src + gx));
-            else v = (uint32_t)__ldg(src + gxa) | ((uint32_t)__ldg(src + gxb) << 16);
-            *reinterpret_cast<uint32_t*>(&S.depth[r][c]) = v;
+            for (int r = 0; r < nRows; ++r) {
+                const int gy = max(0, min(ry0 + r, H - 1));
+                *reinterpret_cast<uint32_t*>(&S.depth[r][c]) = __ldg(reinterpret_cast<const uint32_t*>(rowPtr<uint16_t>(D0, gy) + gx));
+            }
+        } else {
+            for (int r = 0; r < nRows; ++r) {
+                const int gy = max(0, min(ry0 + r, H - 1));
+                const uint16_t* src = rowPtr<uint16_t>(D0, gy);
+                *reinterpret_cast<uint32_t*>(&S.depth[r][c]) = (uint32_t)__ldg(src + gxa) | ((uint32_t)__ldg(src + gxb) << 16);
+            }
         }
     }
 
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
             a = na; d = nb - na;
         }
         if (doZ) {
-            const float A0 = u16ToFloat(zwin[rA][xa]), B0 = u16ToFloat(zwin[rA][xb]), A1 = u16ToFloat(zwin[rB][xa]), B1 = u16ToFloat(zwin[rB][xb]);
+            const float A0 = zwin[rA][xa], B0 = zwin[rA][xb], A1 = zwin[rB][xa], B1 = zwin[rB][xb];
             const float na = fmaf(c.f, B0 - A0, A0), nb = fmaf(c.f, B1 - A1, A1);
             za = na; zd = nb - na;
         }
