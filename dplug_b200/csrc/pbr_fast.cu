@@ -77,6 +77,7 @@ __device__ __forceinline__ F3 fma3(float s, F3 a, F3 b) { return F3{fmaf(s, a.x,
 __device__ __forceinline__ float byteToFloat(uint32_t p, int k) {
     return __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7440 + k)) - 8388608.0f;
 }
+__device__ __forceinline__ float byteBiased23(uint32_t p, int k) { return __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7440 + k)); }   // 2^23 + byte
 __device__ __forceinline__ F3 rgbOf(uint32_t p) { return F3{byteToFloat(p, 0), byteToFloat(p, 1), byteToFloat(p, 2)}; }
 // byte k -> float 32768 + b with a single PRMT (b lands in mantissa bits 8..15 of 2^15).  Used where a weighted
 // sum with weights adding up to 1 follows: the 32768 is subtracted once from the result (absolute error of the
@@ -282,8 +283,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         const Lin c = linCoord(l, opaque(ic), lw);
         const int ox = org[oIdx], xa = c.i0 - ox, xb = c.i1 - ox;
         if (doD) {
-            const F3 A0 = rgbOf(win[rA][xa]), B0 = rgbOf(win[rA][xb]), A1 = rgbOf(win[rB][xa]), B1 = rgbOf(win[rB][xb]);
-            const F3 na = fma3(c.f, B0 - A0, A0), nb = fma3(c.f, B1 - A1, A1);
+            // B - A is taken on the 2^23-biased values (the biases cancel exactly), only A is un-biased
+            const uint32_t tA0 = win[rA][xa], tB0 = win[rA][xb], tA1 = win[rB][xa], tB1 = win[rB][xb];
+            const F3 A0 = rgbOf(tA0), A1 = rgbOf(tA1);
+            const F3 dB0{byteBiased23(tB0, 0) - byteBiased23(tA0, 0), byteBiased23(tB0, 1) - byteBiased23(tA0, 1), byteBiased23(tB0, 2) - byteBiased23(tA0, 2)};
+            const F3 dB1{byteBiased23(tB1, 0) - byteBiased23(tA1, 0), byteBiased23(tB1, 1) - byteBiased23(tA1, 1), byteBiased23(tB1, 2) - byteBiased23(tA1, 2)};
+            const F3 na = fma3(c.f, dB0, A0), nb = fma3(c.f, dB1, A1);
             a = na; d = nb - na;
         }
         if (doZ) {
