@@ -86,6 +86,9 @@ SIGNATURES = {
     "b2pbr_composite_tile": (C.c_int, [C.c_void_p, C.POINTER(box2i), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2pbr_composite_tile_host": (C.c_int, [C.c_void_p, imageref, C.POINTER(box2i), C.c_int, C.POINTER(box2i), C.c_int,
                                             imageref, imageref, imageref]),
+    "b2pbr_composite_tile_host_begin": (C.c_int, [C.c_void_p, imageref, C.POINTER(box2i), C.c_int, C.POINTER(box2i), C.c_int,
+                                                  imageref, imageref, imageref]),
+    "b2pbr_composite_tile_host_end": (C.c_int, [C.c_void_p]),
     "b2pbr_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(box2i), C.c_int]),
     "b2pbr_download_swizzled": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(box2i), C.c_int]),
     "b2_band_need_rows": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_int)] * 2),

@@ -122,6 +122,21 @@ class PBRCompositor:
             self.download(areas, out=wfb)
         return wfb
 
+    def compositeTileBegin(self, wfb, areas, diffuseMap, materialMap, depthMap, updateRects=None):
+        """compositeTile with host images, enqueued only (page-locked images): several compositors — a batch of plug-in
+        UIs — can have their calls in flight together.  The arrays must stay alive and unmodified until compositeTileEnd."""
+        arr = _lib.boxes(areas)
+        upd = _lib.boxes(updateRects) if updateRects is not None else None
+        self._inflight = (wfb, diffuseMap, materialMap, depthMap, arr, upd)
+        _lib.check(self._l.b2pbr_composite_tile_host_begin(self._h, _ref(wfb), arr, len(areas), upd, 0 if updateRects is None else len(updateRects),
+                                                           _ref(diffuseMap), _ref(materialMap), _ref(depthMap)))
+
+    def compositeTileEnd(self):
+        _lib.check(self._l.b2pbr_composite_tile_host_end(self._h))
+        wfb = self._inflight[0]
+        self._inflight = None
+        return wfb
+
     # --- legacy setters, legacypbr.d:75-123 -----------------------------------------------------
     def params(self):
         p = _lib.params()

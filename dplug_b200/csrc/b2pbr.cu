@@ -1180,7 +1180,7 @@ int b2pbr_composite_raw(b2pbr* c, const b2_box2i* areas, int n) {
     return B2_OK;
 }
 
-int b2pbr_download(b2pbr* c, void* host, size_t host_pitch, const b2_box2i* rects, int n) {
+static int pbrDownloadEnqueue(b2pbr* c, void* host, size_t host_pitch, const b2_box2i* rects, int n) {
     if (!c || !c->outAlloc || !host) return fail(B2_ERR_STATE, "download: bad state");
     CU(cudaSetDevice(c->device));
     for (int k = 0; k < n; ++k) {
@@ -1214,6 +1214,11 @@ int b2pbr_download(b2pbr* c, void* host, size_t host_pitch, const b2_box2i* rect
         } else
             CU(cudaMemcpy2DAsync(hp, host_pitch, dp, (size_t)c->out.pitch, rowBytes, (size_t)boxH(r), cudaMemcpyDeviceToHost, c->stream));
     }
+    return B2_OK;
+}
+int b2pbr_download(b2pbr* c, void* host, size_t host_pitch, const b2_box2i* rects, int n) {
+    int rc = pbrDownloadEnqueue(c, host, host_pitch, rects, n);
+    if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
     return B2_OK;
 }
@@ -1246,7 +1251,7 @@ int b2pbr_download_swizzled(b2pbr* c, int pf, void* host, size_t host_pitch, con
 // Same results as the sequential path: the work is only re-ordered (every mip row is generated once, from
 // complete sources; every area is composited once).
 static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, int n_areas,
-                            b2_imageref dI, b2_imageref mI, b2_imageref zI) {
+                            b2_imageref dI, b2_imageref mI, b2_imageref zI, bool wait) {
     const int W = c->W, H = c->H;
     CU(cudaSetDevice(c->device));
     if (!c->sIn) {
@@ -1418,7 +1423,11 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
     }
     c->launches += c->diffuse->launches + c->depth->launches - mipLaunches0;
     if (dbg) { cudaEventRecord(d2, c->stream); cudaEventRecord(d3, c->sOut); }
-    CU(cudaStreamSynchronize(c->sOut));
+    // the copy-back stream joins the compositor's stream, so one wait on c->stream (b2pbr_composite_tile_host_end, or
+    // anything the caller enqueues there) covers the whole call
+    CU(cudaEventRecord(c->pipeEvents[2 * nChunks], c->sOut));
+    CU(cudaStreamWaitEvent(c->stream, c->pipeEvents[2 * nChunks], 0));
+    if (!wait && !dbg) return B2_OK;
     CU(cudaStreamSynchronize(c->stream));
     if (dbg) {
         float a = 0, b = 0, e = 0;
@@ -1435,8 +1444,8 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
     return B2_OK;
 }
 
-int b2pbr_composite_tile_host(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, int n_areas, const b2_box2i* update_rects,
-                              int n_update, b2_imageref diffuse_l0, b2_imageref material_l0, b2_imageref depth_l0) {
+static int pbrCompositeTileHost(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, int n_areas, const b2_box2i* update_rects,
+                                int n_update, b2_imageref diffuse_l0, b2_imageref material_l0, b2_imageref depth_l0, bool wait) {
     if (!c || !c->diffuse) return fail(B2_ERR_STATE, "compositeTile(host) before resizeBuffers");
     if (diffuse_l0.w != c->W || diffuse_l0.h != c->H || material_l0.w != c->W || material_l0.h != c->H ||
         depth_l0.w != c->W || depth_l0.h != c->H || wfb.w != c->W || wfb.h != c->H)
@@ -1446,7 +1455,7 @@ int b2pbr_composite_tile_host(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, 
     // whole frame dirty (first frame, resize, animated UI): overlap PCIe with the kernels
     if (!c->banded && !c->profile && n_update == 1 && update_rects[0].min_x == 0 && update_rects[0].min_y == 0 &&
         update_rects[0].max_x == c->W && update_rects[0].max_y == c->H && c->H >= 512)
-        return pbrHostPipelined(c, wfb, areas, n_areas, diffuse_l0, material_l0, depth_l0);
+        return pbrHostPipelined(c, wfb, areas, n_areas, diffuse_l0, material_l0, depth_l0, wait);
     traceBegin(c, "upload dirty rects");
     if ((rc = b2mip_upload(c->diffuse, 0, diffuse_l0.pixels, diffuse_l0.pitch, update_rects, n_update))) return rc;
     if ((rc = b2mip_upload(c->material, 0, material_l0.pixels, material_l0.pitch, update_rects, n_update))) return rc;
@@ -1455,9 +1464,26 @@ int b2pbr_composite_tile_host(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, 
     if ((rc = b2pbr_regenerate_mipmaps(c, update_rects, n_update))) return rc;
     if ((rc = pbrComposite(c, areas, n_areas, nullptr, nullptr, nullptr))) return rc;
     traceBegin(c, "download composited");
-    rc = b2pbr_download(c, wfb.pixels, wfb.pitch, areas, n_areas);
+    rc = pbrDownloadEnqueue(c, wfb.pixels, wfb.pitch, areas, n_areas);
     traceEnd(c);
-    return rc;
+    if (rc || !wait) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
+int b2pbr_composite_tile_host(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, int n_areas, const b2_box2i* update_rects,
+                              int n_update, b2_imageref diffuse_l0, b2_imageref material_l0, b2_imageref depth_l0) {
+    return pbrCompositeTileHost(c, wfb, areas, n_areas, update_rects, n_update, diffuse_l0, material_l0, depth_l0, true);
+}
+int b2pbr_composite_tile_host_begin(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, int n_areas, const b2_box2i* update_rects,
+                                    int n_update, b2_imageref diffuse_l0, b2_imageref material_l0, b2_imageref depth_l0) {
+    return pbrCompositeTileHost(c, wfb, areas, n_areas, update_rects, n_update, diffuse_l0, material_l0, depth_l0, false);
+}
+int b2pbr_composite_tile_host_end(b2pbr* c) {
+    if (!c) return fail(B2_ERR_INVALID, "null compositor");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2_OK;
 }
 
 int b2_band_need_rows(int W, int H, int y0, int y1, int map, int level, int* need_lo, int* need_hi) {

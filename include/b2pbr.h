@@ -196,6 +196,13 @@ int b2pbr_composite_tile(b2pbr*, const b2_box2i* areas, int n, b2mip* diffuse, b
 int b2pbr_composite_tile_host(b2pbr*, b2_imageref wfb, const b2_box2i* areas, int n_areas,
                               const b2_box2i* update_rects, int n_update,
                               b2_imageref diffuse_l0, b2_imageref material_l0, b2_imageref depth_l0);
+/* The same call split in two for callers that drive SEVERAL compositors (a batch of plug-in instance UIs): _begin
+ * enqueues the whole call (uploads, device mips, tiles, copy-back) and returns; _end waits until `wfb` holds the frame.
+ * The images must stay valid and unmodified until _end; asynchronous only for page-locked images (pageable memory makes
+ * the copies synchronous).  One call in flight per compositor. */
+int b2pbr_composite_tile_host_begin(b2pbr*, b2_imageref wfb, const b2_box2i* areas, int n_areas, const b2_box2i* update_rects,
+                                    int n_update, b2_imageref diffuse_l0, b2_imageref material_l0, b2_imageref depth_l0);
+int b2pbr_composite_tile_host_end(b2pbr*);
 
 /* device -> host copy of rectangles of the composited buffer; synchronises */
 int b2pbr_download(b2pbr*, void* host, size_t host_pitch, const b2_box2i* rects, int n);

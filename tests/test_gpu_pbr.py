@@ -308,6 +308,42 @@ def test_page_locked_host_images(b2):
             l.b2_host_unregister(b.ctypes.data_as(C.c_void_p))
 
 
+@pytest.mark.parametrize("W,H", [(320, 200), (1000, 700)])
+def test_host_call_begin_end(b2, W, H):
+    """compositeTileBegin / End (a batch of UIs with their host calls in flight together) == the synchronous call."""
+    import ctypes as C
+    from dplug_b200 import _lib
+    l = _lib.lib()
+    tiles = b2.tileAreas([(0, 0, W, H)], 64, 64)
+    frames = [synth.frame(W, H, synth.SEED + k) for k in range(3)]
+    want = []
+    ref = b2.PBRCompositor(0); ref.resizeBuffers(W, H); ref.setSkybox(synth.skybox(128, 96))
+    for d, m, z in frames:
+        out = np.zeros((H, W, 4), np.uint8)
+        ref.compositeTile(out, tiles, d, m, z, updateRects=[(0, 0, W, H)])
+        want.append(out)
+    pinned = []
+    comps = []
+    try:
+        for d, m, z in frames:
+            bufs = [d.copy(), m.copy(), z.copy(), np.zeros((H, W, 4), np.uint8)]
+            for b in bufs:
+                assert l.b2_host_register(b.ctypes.data_as(C.c_void_p), b.nbytes) == 0
+                pinned.append(b)
+            c = b2.PBRCompositor(0); c.resizeBuffers(W, H); c.setSkybox(synth.skybox(128, 96))
+            comps.append((c, bufs))
+        for rep in range(2):
+            for c, (d, m, z, out) in comps:
+                out[...] = 0
+                c.compositeTileBegin(out, tiles, d, m, z, updateRects=[(0, 0, W, H)])
+            for k, (c, bufs) in enumerate(comps):
+                assert c.compositeTileEnd() is bufs[3]
+                assert np.array_equal(bufs[3], want[k]), (rep, k)
+    finally:
+        for b in pinned:
+            l.b2_host_unregister(b.ctypes.data_as(C.c_void_p))
+
+
 def test_cuda_graph_replay(b2):
     """A frame recorded with graphBegin/graphEnd replays to the same bytes, also after the inputs changed."""
     W, H = 512, 384
