@@ -113,9 +113,11 @@ __device__ __forceinline__ uint32_t cvtSatU8(float f) {  // truncate, clamp to [
 // RSQRTSS emulation for operands that are provably positive normal floats (all three uses here): the table entry of
 // the bin with the exponent moved by floor((e - 126) / 2) = (bits >> 24) - 63, i.e. entry + (63 << 23) - ((bits >> 1)
 // & 0x7f800000).  Same value as rsqrtss_x86() on that domain; a zero operand yields +inf like the instruction.
+template <bool MAY_BE_ZERO = true>
 __device__ __forceinline__ float rsqrtssPos(const uint32_t* __restrict__ tab, float x) {
     const uint32_t b = __float_as_uint(x);
     const uint32_t r = __ldg(tab + ((b >> 13) & 0x7ffu)) + 0x1F800000u - ((b >> 1) & 0x7F800000u);
+    if (!MAY_BE_ZERO) return __uint_as_float(r);   // operand bounded away from zero by construction
     return b == 0u ? __uint_as_float(0x7f800000u) : __uint_as_float(r);
 }
 
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
             float yz = __fadd_rn(__fadd_rn(__fadd_rn(yz0, yz1), yz2), yz3);
             float vx = -xz, vy = yz;
             float len2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), nz2);  // (+ w*w = +0 dropped)
-            float inv = rsqrtssPos(P.rsqrtTab, len2);
+            float inv = rsqrtssPos<false>(P.rsqrtTab, len2);   // len2 >= 0.3827^2
             nx = vx * inv; ny = vy * inv; nzc = 0.382658847856f * inv;
             // variance (legacypbr.d:356-377): second differences of the 3x3 window.  The reference sums raw depths
             // (exact); here they are rebuilt from d (relative error ~1e-7, the variance feeds no RSQRTSS)
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2_MIN_CTAS) k_pbr_fast(co
         if (mask & 0x30u) {
             ey = rs.ey;
             float len2 = __fadd_rn(__fadd_rn(eyeX2, rs.ey2), 1.0f);
-            float inv = rsqrtssPos(P.rsqrtTab, len2);
+            float inv = rsqrtssPos<false>(P.rsqrtTab, len2);   // len2 >= 1
             ex = __fmul_rn(eyeX, inv); ey = __fmul_rn(ey, inv); ez = inv;  // 1.0f * inv
         }
 
