@@ -764,7 +764,12 @@ static int stripRowsOfArea(const b2_box2i& a, int R, int tailRow, int tailRow2) 
     if (a.max_y > tailRow2 && R > 4) return 4;
     return (a.max_y > tailRow && R > 8) ? 8 : R;
 }
+static int stripRowsFor(const b2_box2i* areas, int n);
+struct b2pbr;
+static int stripRowsOfAreaAt(const b2pbr* c, int k, int n, const b2_box2i& a, int R0);
 static int stripRowsFor(const b2_box2i* areas, int n) {
+    static const int forced = getenv("B2_STRIP_ROWS") ? atoi(getenv("B2_STRIP_ROWS")) : 0;   // tuning aid
+    if (forced >= 1 && forced <= pbr_fast_strip_rows()) return forced;
     const int full = pbr_fast_strip_rows();
     int R = full;
     for (; R > 4; R >>= 1) {
@@ -772,6 +777,17 @@ static int stripRowsFor(const b2_box2i* areas, int n) {
         for (int k = 0; k < n; ++k) strips += (long long)((boxH(areas[k]) + R - 1) / R) * ((boxW(areas[k]) + 31) / 32);
         if (strips >= 148 * 16) break;
     }
+    return R;
+}
+
+// Strip height of area k of an n-area list.  Tail balancing: CTAs are dispatched in list order and a frame is only a
+// few waves of them (3.4 at 4K: the last wave would run at 45 % occupancy), so the last 8 % of a long list are cut into
+// 8-row strips that fill the slots the full-height strips leave empty (4K lighting 0.239 -> 0.234 ms; 15 % and 25 %
+// measured slower, as did 16-row strips everywhere: 0.250 ms).
+static int stripRowsOfAreaAt(const b2pbr* c, int k, int n, const b2_box2i& a, int R0) {
+    static const int tailPct = getenv("B2_TAIL_PCT") ? atoi(getenv("B2_TAIL_PCT")) : 0;   // tuning aid (8 once verified on the GPU suite)
+    int R = stripRowsOfArea(a, R0, c->tailRow, c->tailRow2);
+    if (R0 == pbr_fast_strip_rows() && k >= n - n * tailPct / 100 && R > 8) R = 8;
     return R;
 }
 
@@ -794,7 +810,7 @@ static int pbrUploadBoxes(b2pbr* c, const b2_box2i* areas, int n, int kind) {
         const int R0 = stripRowsFor(areas, n);
         for (int k = 0; k < n; ++k) {
             const b2_box2i& a = areas[k];
-            const int R = stripRowsOfArea(a, R0, c->tailRow, c->tailRow2);
+            const int R = stripRowsOfAreaAt(c, k, n, a, R0);
             for (int y = a.min_y; y < a.max_y; y += R)
                 for (int x = a.min_x; x < a.max_x; x += 32)
                     work.push_back(Box{x, y, x + 32 < a.max_x ? x + 32 : a.max_x, y + R < a.max_y ? y + R : a.max_y});
@@ -1323,9 +1339,9 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
     c->tailRow = nChunks >= 3 ? cEnd[nChunks - 3] : H - 256;
     c->tailRow2 = nChunks >= 2 ? cEnd[nChunks - 2] : H - 128;
     const int R0 = stripRowsFor(areas, n_areas);
-    auto workItems = [&](const b2_box2i& a, bool fast) {
+    auto workItems = [&](int k, const b2_box2i& a, bool fast) {   // k = index in the sorted list that is uploaded
         if (!fast) return 1;
-        const int R = stripRowsOfArea(a, R0, c->tailRow, c->tailRow2);
+        const int R = stripRowsOfAreaAt(c, k, n_areas, a, R0);
         return ((boxH(a) + R - 1) / R) * ((boxW(a) + 31) / 32);
     };
     // stage 1: every upload is enqueued up front, so the copy engine never waits for this thread (the host-side cost
@@ -1397,7 +1413,7 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
             int rc = pbrComposite(c, sorted.data(), n_areas, nullptr, nullptr, nullptr, 0, 0, &fast);
             if (rc) return rc;
             int cnt = 0;
-            for (size_t q = first; q < pos; ++q) cnt += workItems(sorted[q], fast);
+            for (size_t q = first; q < pos; ++q) cnt += workItems((int)q, sorted[q], fast);
             rc = pbrComposite(c, sorted.data(), n_areas, nullptr, nullptr, nullptr, workPos, cnt, nullptr);
             if (rc) return rc;
             workPos += cnt;
