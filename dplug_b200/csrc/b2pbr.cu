@@ -785,7 +785,7 @@ static int stripRowsFor(const b2_box2i* areas, int n) {
 // 8-row strips that fill the slots the full-height strips leave empty (4K lighting 0.239 -> 0.234 ms; 15 % and 25 %
 // measured slower, as did 16-row strips everywhere: 0.250 ms).
 static int stripRowsOfAreaAt(const b2pbr* c, int k, int n, const b2_box2i& a, int R0) {
-    static const int tailPct = getenv("B2_TAIL_PCT") ? atoi(getenv("B2_TAIL_PCT")) : 0;   // tuning aid (8 once verified on the GPU suite)
+    static const int tailPct = getenv("B2_TAIL_PCT") ? atoi(getenv("B2_TAIL_PCT")) : 8;   // tuning aid
     int R = stripRowsOfArea(a, R0, c->tailRow, c->tailRow2);
     if (R0 == pbr_fast_strip_rows() && k >= n - n * tailPct / 100 && R > 8) R = 8;
     return R;
