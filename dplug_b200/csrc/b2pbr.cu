@@ -17,7 +17,7 @@
 #include "host_rects.hpp"
 
 namespace b2 {
-// kernels (mip_kernels.cu, pbr_exact.cu, pbr_fast.cu)
+// kernels (mip_kernels.cu, mip_fused.cu, pbr_exact.cu, pbr_fast.cu)
 void launch_box_rgba(const DevLevel& dst, const DevLevel& src, Box r, bool premul, cudaStream_t s);
 void launch_box_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
 void launch_cubic_rgba(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
