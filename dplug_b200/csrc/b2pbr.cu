@@ -642,6 +642,14 @@ struct b2pbr {
     float shadowW[11]; float shadowInvTotal;
 };
 
+// Recorded graphs bake device addresses (maps, skybox, output) and the pass parameters into their kernel arguments:
+// whatever frees or changes those destroys the recordings; b2pbr_graph_launch then fails with B2_ERR_STATE.
+static void pbrInvalidateGraphs(b2pbr* c) {
+    for (auto& g : c->graphs)
+        if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    for (auto& wl : c->workLists) wl.pinned = false;
+}
+
 static void pbrConstants(b2pbr* c) {
     // PassObliqueShadowLight's compile-time tables (gui/dplug/gui/legacypbr.d:469-490): fallOff ^^ k and
     // the normalisation, evaluated in double and narrowed once.
@@ -1010,6 +1018,7 @@ int b2pbr_resize(b2pbr* c, int width, int height, int tw, int th) {
     if (!c || width <= 0 || height <= 0 || tw <= 0 || th <= 0) return fail(B2_ERR_INVALID, "resizeBuffers: bad arguments");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    pbrInvalidateGraphs(c);
     pbrFreeMaps(c);
     for (auto& wl : c->workLists) { wl.key.clear(); wl.kind = -1; wl.pinned = false; }   // strip cuts depend on the size
     c->W = width; c->H = height; c->tileW = tw; c->tileH = th;
@@ -1045,11 +1054,13 @@ int b2pbr_resize(b2pbr* c, int width, int height, int tw, int th) {
 
 int b2pbr_set_params(b2pbr* c, const b2pbr_params* p) {
     if (!c || !p) return fail(B2_ERR_INVALID, "set_params: null");
+    if (memcmp(&c->params, p, sizeof(*p)) != 0) pbrInvalidateGraphs(c);
     c->params = *p;
     return B2_OK;
 }
 int b2pbr_set_mode(b2pbr* c, int mode) {
     if (!c || (mode != B2_MODE_FAST && mode != B2_MODE_EXACT)) return fail(B2_ERR_INVALID, "set_mode: bad arguments");
+    if (mode != c->mode) pbrInvalidateGraphs(c);
     c->mode = mode;
     return B2_OK;
 }
@@ -1063,6 +1074,7 @@ int b2pbr_set_skybox(b2pbr* c, const uint8_t* rgba, int w, int h, size_t pitch) 
     if (!c) return fail(B2_ERR_INVALID, "null compositor");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    pbrInvalidateGraphs(c);
     b2mip_destroy(c->sky);
     c->sky = nullptr;
     if (!rgba) return B2_OK;
@@ -1187,6 +1199,13 @@ int b2pbr_composite_tile(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse,
 int b2pbr_composite_raw(b2pbr* c, const b2_box2i* areas, int n) {
     if (!c || !c->outAlloc || (n > 0 && !areas)) return fail(B2_ERR_STATE, "composite_raw: bad state");
     if (n <= 0) return B2_OK;
+    for (int k = 0; k < n; ++k) {   // same validation as compositeTile
+        const b2_box2i& a = areas[k];
+        if (!boxSorted(a) || a.min_x < 0 || a.min_y < 0 || a.max_x > c->W || a.max_y > c->H)
+            return fail(B2_ERR_INVALID, "composite_raw: area outside the frame");
+        if (!boxEmpty(a) && (a.min_y < c->out.y0 || a.max_y > c->out.y0 + c->out.rows))
+            return fail(B2_ERR_INVALID, "composite_raw: area outside this band");
+    }
     CU(cudaSetDevice(c->device));
     int rc = pbrUploadBoxes(c, areas, n, 0);
     if (rc) return rc;
@@ -1466,7 +1485,18 @@ static int pbrCompositeTileHost(b2pbr* c, b2_imageref wfb, const b2_box2i* areas
     if (diffuse_l0.w != c->W || diffuse_l0.h != c->H || material_l0.w != c->W || material_l0.h != c->H ||
         depth_l0.w != c->W || depth_l0.h != c->H || wfb.w != c->W || wfb.h != c->H)
         return fail(B2_ERR_INVALID, "compositeTile(host): image size differs from resizeBuffers size");
-    if (!update_rects) { update_rects = areas; n_update = n_areas; }
+    // The reference hands compositeTile only the tile list (compositor.d:63-68): with update_rects == NULL the areas
+    // are what changed.  Either way the list is coalesced first (a full-frame 64x64 tile list becomes ONE rectangle):
+    // regenerating the union of adjacent rectangles recomputes exactly the texels the separate rectangles would
+    // (impactOnNextLevel of a union of adjacent boxes is the union of their impacts, and every regenerated texel is a
+    // pure function of the level below), so the uploads, the mip chain and the whole-frame test see few large boxes.
+    std::vector<b2_box2i> coalesced;
+    if (!update_rects) mergeRects(areas, n_areas, coalesced);
+    else {
+        if (n_update < 0) return fail(B2_ERR_INVALID, "compositeTile(host): negative update rectangle count");
+        mergeRects(update_rects, n_update, coalesced);
+    }
+    update_rects = coalesced.data(); n_update = (int)coalesced.size();
     int rc;
     // whole frame dirty (first frame, resize, animated UI): overlap PCIe with the kernels
     if (!c->banded && !c->profile && n_update == 1 && update_rects[0].min_x == 0 && update_rects[0].min_y == 0 &&
@@ -1560,7 +1590,8 @@ int b2pbr_graph_end(b2pbr* c, int* graph_id) {
     return B2_OK;
 }
 int b2pbr_graph_launch(b2pbr* c, int graph_id) {
-    if (!c || graph_id < 0 || graph_id >= (int)c->graphs.size() || !c->graphs[graph_id]) return fail(B2_ERR_INVALID, "graph_launch: bad id");
+    if (!c || graph_id < 0 || graph_id >= (int)c->graphs.size()) return fail(B2_ERR_INVALID, "graph_launch: bad id");
+    if (!c->graphs[graph_id]) return fail(B2_ERR_STATE, "graph_launch: the recording was invalidated by resizeBuffers / setSkybox / set_params / set_mode; record it again");
     CU(cudaGraphLaunch(c->graphs[graph_id], c->stream));
     c->launches += c->graphLaunches[graph_id];
     return B2_OK;

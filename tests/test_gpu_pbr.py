@@ -370,3 +370,84 @@ def test_cuda_graph_replay(b2):
             c.compositeTile(None, b2.tileAreas([(0, 0, W, H)], 32, 32))
         finally:
             c.graphEnd()
+
+
+@pytest.mark.parametrize("W,H,bound", [(620, 330, 8), (3840, 2160, 40)])
+def test_shim_call_shape_launch_count(b2, W, H, bound):
+    """The call the D shim makes (d/dplug/gui/cudacompositor.d: update_rects = NULL, the 64x64 tile list of the whole
+    frame, gui/dplug/gui/graphics.d:1338-1349): the tile list is coalesced into one rectangle, so the mip chain takes
+    the fused launches (and, at 4K, the pipelined path) instead of one launch per level and tile.  Pageable images:
+    the copies are DMA, so every counted launch is mip or lighting work.  620x330: 2 + 2 fused mip launches + lighting;
+    3840x2160: four pipeline stages x (two pyramids + lighting)."""
+    d, m, z = synth.frame(W, H)
+    c = b2.PBRCompositor(0); c.resizeBuffers(W, H); c.setSkybox(synth.skybox(128, 96))
+    tiles = b2.tileAreas([(0, 0, W, H)], 64, 64)
+    wfb = np.zeros((H, W, 4), np.uint8)
+    c.compositeTile(wfb, tiles, d, m, z)                      # updateRects=None -> NULL, like the shim
+    n0 = c.kernelLaunches()
+    c.compositeTile(wfb, tiles, d, m, z)
+    n = c.kernelLaunches() - n0
+    assert n <= bound, "%d kernel launches for one full-frame host call at %dx%d" % (n, W, H)
+    want = np.zeros((H, W, 4), np.uint8)
+    c.compositeTile(want, tiles, d, m, z, updateRects=[(0, 0, W, H)])
+    assert np.array_equal(wfb, want)
+
+
+def test_null_update_rects_partial_tiles(b2, oracle):
+    """NULL update_rects with a tile list that is NOT the whole frame (tiles of two grown dirty rectangles): same bytes
+    as passing the rectangles themselves as the update list."""
+    W, H = 700, 500
+    d, m, z = synth.frame(W, H)
+    sky = synth.skybox(128, 96)
+    a = b2.PBRCompositor(0); a.resizeBuffers(W, H); a.setSkybox(sky)
+    b = b2.PBRCompositor(0); b.resizeBuffers(W, H); b.setSkybox(sky)
+    whole = b2.tileAreas([(0, 0, W, H)], 64, 64)
+    wa, wb = np.zeros((H, W, 4), np.uint8), np.zeros((H, W, 4), np.uint8)
+    a.compositeTile(wa, whole, d, m, z); b.compositeTile(wb, whole, d, m, z, updateRects=[(0, 0, W, H)])
+    assert np.array_equal(wa, wb)
+    d2, m2, z2 = synth.frame(W, H, synth.SEED + 4)
+    rects = [(30, 40, 250, 210), (400, 260, 640, 470)]
+    for r in rects:
+        ys, xs = slice(r[1], r[3]), slice(r[0], r[2])
+        d[ys, xs] = d2[ys, xs]; m[ys, xs] = m2[ys, xs]; z[ys, xs] = z2[ys, xs]
+    tiles = b2.tileAreas(rects, 64, 64)
+    a.compositeTile(wa, tiles, d, m, z)
+    b.compositeTile(wb, tiles, d, m, z, updateRects=rects)
+    assert np.array_equal(wa, wb)
+    ref = oracle.Graphics(W, H, numThreads=8); ref.setSkybox(sky); ref.setInputs(d, m, z)
+    ref.regenerateMipmaps([(0, 0, W, H)]); ref.compositeGUI(rects)
+    exp = np.array(ref.output())
+    for r in rects:
+        _compare(wa[r[1]:r[3], r[0]:r[2]], exp[r[1]:r[3], r[0]:r[2]], "NULL update list %s" % (r,))
+
+
+def test_graph_invalidation_and_raw_bounds(b2):
+    """A recorded frame bakes buffer addresses and parameters into its kernels: resizeBuffers / setSkybox / set_params
+    invalidate it (launch fails instead of replaying on freed memory).  composite_raw validates its areas."""
+    W, H = 256, 192
+    d, m, z = synth.frame(W, H)
+    c = b2.PBRCompositor(0); c.resizeBuffers(W, H); c.setSkybox(synth.skybox(128, 96))
+    tiles = b2.BoxArray(b2.tileAreas([(0, 0, W, H)], 64, 64)); whole = b2.BoxArray([(0, 0, W, H)])
+    c.diffuseMap.upload(0, d); c.materialMap.upload(0, m); c.depthMap.upload(0, z)
+
+    def record():
+        c.regenerateMipmaps(whole); c.compositeTile(None, tiles)
+        c.graphBegin(); c.regenerateMipmaps(whole); c.compositeTile(None, tiles)
+        return c.graphEnd()
+
+    g = record(); c.graphLaunch(g)
+    c.ambientLight(0.2)
+    with pytest.raises(b2.B2Error):
+        c.graphLaunch(g)
+    g = record(); c.graphLaunch(g)
+    c.setSkybox(synth.skybox(64, 48))
+    with pytest.raises(b2.B2Error):
+        c.graphLaunch(g)
+    g = record(); c.graphLaunch(g)
+    c.resizeBuffers(W, H)
+    with pytest.raises(b2.B2Error):
+        c.graphLaunch(g)
+    c.sync()
+    for bad in [(0, 0, W + 1, 10), (-1, 0, 10, 10), (0, H - 4, 8, H + 4)]:
+        with pytest.raises(b2.B2Error):
+            c.compositeRaw([bad])
