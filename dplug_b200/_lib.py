@@ -93,6 +93,18 @@ SIGNATURES = {
     "b2pbr_download_swizzled": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(box2i), C.c_int]),
     "b2_band_need_rows": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_int)] * 2),
     "b2pbr_band_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4),
+    "b2_band_rows": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_int)] * 2),
+    "b2_band_plan": (C.c_int, [C.c_int] * 5 + [C.POINTER(box2i)] + [C.POINTER(C.c_int)] * 3),
+    "b2_band_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "b2band_create_nccl": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]),
+    "b2band_create_peers": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]),
+    "b2band_destroy": (None, [C.c_void_p]),
+    "b2band_exchange_begin": (C.c_int, [C.c_void_p]),
+    "b2band_exchange_end": (C.c_int, [C.c_void_p]),
+    "b2band_composite_frame": (C.c_int, [C.c_void_p]),
+    "b2band_sync": (C.c_int, [C.c_void_p]),
+    "b2band_halo_bytes_per_frame": (C.c_uint64, [C.c_void_p]),
+    "b2band_info": (C.c_int, [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 5),
     "b2pbr_graph_begin": (C.c_int, [C.c_void_p]),
     "b2pbr_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "b2pbr_graph_launch": (C.c_int, [C.c_void_p, C.c_int]),

@@ -34,7 +34,7 @@ def _stale(target, deps):
 
 def build_lib(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "nvcc")
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp", ".inc"))]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp", ".inc", ".inl"))]
     headers.append(os.path.join(HERE, "..", "include", "b2pbr.h"))
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)

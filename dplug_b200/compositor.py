@@ -239,6 +239,18 @@ class PBRCompositor:
             _lib.check(self._l.b2pbr_download(self._h, C.c_void_p(origin), out.strides[0], _lib.boxes([(0, row0, self.width, row1)]), 1))
         return out
 
+    def downloadRowsInto(self, out, row0, row1):
+        """rows [row0, row1) of the composited buffer into `out` ((row1 - row0, width, 4) uint8, e.g. pinned); synchronises"""
+        origin = out.ctypes.data - row0 * out.strides[0]
+        _lib.check(self._l.b2pbr_download(self._h, C.c_void_p(origin), out.strides[0], _lib.boxes([(0, row0, self.width, row1)]), 1))
+        return out
+
+    def outputInfo(self):
+        """device ImageRef of the composited buffer: {"w", "h", "pitch", "pixels"} (pixels = device address of the first stored row)"""
+        r = _lib.imageref()
+        _lib.check(self._l.b2pbr_output(self._h, C.byref(r)))
+        return {"w": r.w, "h": r.h, "pitch": int(r.pitch), "pixels": int(r.pixels)}
+
     def bandRows(self, which, level=0):
         """(stored_lo, stored_hi, need_lo, need_hi) rows of a pyramid level (see b2pbr_band_rows)."""
         v = [C.c_int() for _ in range(4)]

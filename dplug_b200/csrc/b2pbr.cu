@@ -193,6 +193,17 @@ static int mipCheckRect(const b2mip* m, int level, const b2_box2i& r, const char
     return B2_OK;
 }
 
+// the source rows a destination rectangle needs must be stored too (only relevant for row bands)
+static int mipCheckSourceRows(const b2mip* m, int level, int quality, const b2_box2i& r) {
+    const DevLevel& src = m->levels[level - 1];
+    int lo = quality == B2_QUALITY_CUBIC ? 2 * r.min_y - 1 : 2 * r.min_y;
+    int hi = quality == B2_QUALITY_CUBIC ? 2 * (r.max_y - 1) + 2 : 2 * (r.max_y - 1) + 1;
+    if (lo < 0) lo = 0;
+    if (hi > src.h - 1) hi = src.h - 1;
+    if (lo < src.y0 || hi >= src.y0 + src.rows) return fail(B2_ERR_INVALID, "generateLevel: source rows outside the band's halo");
+    return B2_OK;
+}
+
 static int mipGenerateLevel(b2mip* m, int level, int quality, b2_box2i r) {
     if (level < 1 || level >= (int)m->levels.size()) return fail(B2_ERR_INVALID, "generateLevel: level out of range");
     // a degenerate rectangle makes every reference loop a no-op (mipmap.d:683,771,830,906,1046); Box.intersection
@@ -202,14 +213,7 @@ static int mipGenerateLevel(b2mip* m, int level, int quality, b2_box2i r) {
     if (rc) return rc;
     const DevLevel& dst = m->levels[level];
     const DevLevel& src = m->levels[level - 1];
-    // the source rows a destination row needs must be stored too (only relevant for row bands)
-    {
-        int lo = quality == B2_QUALITY_CUBIC ? 2 * r.min_y - 1 : 2 * r.min_y;
-        int hi = quality == B2_QUALITY_CUBIC ? 2 * (r.max_y - 1) + 2 : 2 * (r.max_y - 1) + 1;
-        if (lo < 0) lo = 0;
-        if (hi > src.h - 1) hi = src.h - 1;
-        if (lo < src.y0 || hi >= src.y0 + src.rows) return fail(B2_ERR_INVALID, "generateLevel: source rows outside the band's halo");
-    }
+    if ((rc = mipCheckSourceRows(m, level, quality, r))) return rc;
     CU(cudaSetDevice(m->device));
     if (m->color == B2_COLOR_RGBA8) {
         if (quality == B2_QUALITY_BOX) launch_box_rgba(dst, src, toBox(r), false, m->stream);
@@ -231,12 +235,6 @@ static int mipGenerateLevel(b2mip* m, int level, int quality, b2_box2i r) {
 static bool g_mipFusion = true;
 static long long g_mipFuseBelow = 1ll << 20;   // source levels up to this many texels start a fused group
 
-static bool mipWhole(const b2mip* m) {   // every level stores all of its rows (not a row band)
-    for (const DevLevel& L : m->levels)
-        if (L.y0 != 0 || L.rows != L.h) return false;
-    return true;
-}
-
 static int mipGenerateGroup(b2mip* m, int first, int n, const int* q, const b2_box2i* rects) {
     FusedArgs a{};
     a.n = n;
@@ -252,6 +250,7 @@ static int mipGenerateGroup(b2mip* m, int first, int n, const int* q, const b2_b
         const b2_box2i& r = rects[k];
         if (boxW(r) <= 0 || boxH(r) <= 0) { a.upd[k] = Box{0, 0, 0, 0}; continue; }   // a no-op in the reference
         if (int rc = mipCheckRect(m, first + k, r, "generateLevel")) return rc;
+        if (int rc = mipCheckSourceRows(m, first + k, q[k], r)) return rc;
         a.upd[k] = toBox(r);
     }
     // tiles of the last level owning a texel of some rectangle: the rectangles' ancestors (the odd last column / row
@@ -285,10 +284,11 @@ static int mipGenerateGroup(b2mip* m, int first, int n, const int* q, const b2_b
     return B2_OK;
 }
 
-// levels first .. first + n - 1, in launches of up to three levels (or level by level for row bands / fusion off)
+// levels first .. first + n - 1, in launches of up to three levels (or level by level with fusion off); row bands
+// take the same launches (the fused kernel clips its regions to the rows a band stores)
 static int mipGenerateLevels(b2mip* m, int first, int n, const int* q, const b2_box2i* rects, bool fuseAll = false) {
     if (first < 1 || n < 0 || first + n > (int)m->levels.size()) return fail(B2_ERR_INVALID, "generateLevel: level out of range");
-    if (!g_mipFusion || !mipWhole(m)) {
+    if (!g_mipFusion) {
         for (int k = 0; k < n; ++k) {
             int rc = mipGenerateLevel(m, first + k, q[k], rects[k]);
             if (rc) return rc;
@@ -1107,10 +1107,65 @@ int b2pbr_output(b2pbr* c, b2_imageref* out) {
     return B2_OK;
 }
 
+// One pyramid of regenerateMipmaps (graphics.d:1378-1419): `q[l-1]` = quality of level l, `need` = rows a band has to
+// regenerate per level (nullptr: unbanded).
+//
+// The reference walks level-major: every rectangle of level l before level l + 1.  A rectangle's whole chain may run
+// before the next rectangle's (rect-major: fused launches, up to three levels each) exactly when no rectangle's
+// level-l source footprint can see another rectangle's level-l update: the chains, grown by the cubic reach, are
+// pairwise disjoint on every level.  One rectangle (a full redraw, most interactive redraws, a band's own rows) and
+// far-apart widgets (or a band's two halo rectangles) qualify; overlapping footprints keep the reference order,
+// one launch per level and rectangle.
+static int pbrRegeneratePyramid(b2pbr* c, b2mip* m, const int* q, const int (*need)[2], const b2_box2i* rects, int n) {
+    const int nl = (int)m->levels.size() - 1;
+    if (nl <= 0 || n <= 0) return B2_OK;
+    std::vector<b2_box2i> chain((size_t)n * nl);      // chain[r * nl + l - 1] = update rectangle of level l for rectangle r
+    for (int r = 0; r < n; ++r) {
+        b2_box2i area = rects[r];
+        for (int l = 1; l <= nl; ++l) {
+            const DevLevel& Pv = m->levels[l - 1];
+            area = impactOnNextLevel(q[l - 1], area, Pv.w, Pv.h);
+            chain[(size_t)r * nl + l - 1] = area;
+        }
+    }
+    auto clipped = [&](int r, int l) {   // a band only regenerates the rows it reads (its neighbours own the others)
+        b2_box2i b = chain[(size_t)r * nl + l - 1];
+        if (need) {
+            if (b.min_y < need[l][0]) b.min_y = need[l][0];
+            if (b.max_y > need[l][1]) b.max_y = need[l][1];
+            if (b.max_y <= b.min_y) b = b2_box2i{0, 0, 0, 0};
+        }
+        return b;
+    };
+    bool independent = n <= 16;           // the pair test is quadratic; long lists keep the reference order
+    for (int i = 0; i < n && independent; ++i)
+        for (int j = 0; j < n && independent; ++j) {
+            if (i == j) continue;
+            for (int l = 1; l <= nl; ++l) {
+                const b2_box2i a = chain[(size_t)i * nl + l - 1], b = chain[(size_t)j * nl + l - 1];
+                if (boxW(a) <= 0 || boxH(a) <= 0 || boxW(b) <= 0 || boxH(b) <= 0) continue;
+                const int reach = 4;      // [1 3 3 1] reads 2x-1 .. 2x+2: within 3 texels of the rectangle one level down
+                if (a.min_x - reach < b.max_x && b.min_x < a.max_x + reach && a.min_y - reach < b.max_y && b.min_y < a.max_y + reach) { independent = false; break; }
+            }
+        }
+    if (independent) {
+        std::vector<b2_box2i> lv(nl);
+        for (int r = 0; r < n; ++r) {
+            for (int l = 1; l <= nl; ++l) lv[l - 1] = clipped(r, l);
+            if (int rc = mipGenerateLevels(m, 1, nl, q, lv.data())) return rc;
+        }
+        return B2_OK;
+    }
+    for (int l = 1; l <= nl; ++l)
+        for (int r = 0; r < n; ++r)
+            if (int rc = mipGenerateLevel(m, l, q[l - 1], clipped(r, l))) return rc;
+    return B2_OK;
+}
+
 int b2pbr_regenerate_mipmaps(b2pbr* c, const b2_box2i* rects, int n) {
     if (!c || !c->diffuse) return fail(B2_ERR_STATE, "regenerateMipmaps before resize");
     if (n <= 0) return B2_OK;  // graphics.d:1358-1360
-    std::vector<b2_box2i> s0(rects, rects + n), s1(rects, rects + n);
+    if (!rects) return fail(B2_ERR_INVALID, "regenerateMipmaps: null rectangle list");
     uint64_t before = c->diffuse->launches + c->depth->launches;
     CU(cudaSetDevice(c->device));
     // The two pyramids are independent (the reference builds them one after the other on one thread,
@@ -1122,53 +1177,15 @@ int b2pbr_regenerate_mipmaps(b2pbr* c, const b2_box2i* rects, int n) {
         CU(cudaStreamWaitEvent(c->sAux, c->evFork, 0));
         c->depth->stream = c->sAux;
     }
-    int err = B2_OK;
-    // one dirty rectangle on an unbanded canvas (the full-frame case, and most interactive redraws): the whole chain
-    // of a pyramid goes through the fused launches.  Several rectangles keep the reference's level-major order
-    // (graphics.d:1378-1419: all rectangles of a level before the next level), one launch per level and rectangle.
-    const bool fused = (n == 1) && !c->banded;
+    int qD[kMaxDiffuseLevels], qZ[kMaxDepthLevels];
+    for (int level = 1; level < kMaxDiffuseLevels; ++level) qD[level - 1] = level == 1 ? B2_QUALITY_BOX_ALPHACOV_PREMUL : B2_QUALITY_CUBIC;  // graphics.d:1380-1384
+    for (int level = 1; level < kMaxDepthLevels; ++level) qZ[level - 1] = level >= 3 ? B2_QUALITY_CUBIC : B2_QUALITY_BOX;                   // graphics.d:1414
     traceBegin(c, "diffuse mipmap");
-    if (fused) {
-        int q[kMaxDiffuseLevels];
-        const int nl = (int)c->diffuse->levels.size() - 1;
-        for (int level = 1; level <= nl; ++level) q[level - 1] = level == 1 ? B2_QUALITY_BOX_ALPHACOV_PREMUL : B2_QUALITY_CUBIC;
-        err = b2mip_generate_levels(c->diffuse, 1, nl, q, rects[0], nullptr);
-    }
-    for (int level = 1; !fused && level < (int)c->diffuse->levels.size() && !err; ++level) {
-        int q = level == 1 ? B2_QUALITY_BOX_ALPHACOV_PREMUL : B2_QUALITY_CUBIC;  // graphics.d:1380-1384
-        for (auto& area : s0) {
-            const DevLevel& Pv = c->diffuse->levels[level - 1];
-            area = impactOnNextLevel(q, area, Pv.w, Pv.h);
-            b2_box2i r = area;
-            if (c->banded) {  // a band only regenerates the rows it reads (its neighbours own the others)
-                if (r.min_y < c->needD[level][0]) r.min_y = c->needD[level][0];
-                if (r.max_y > c->needD[level][1]) r.max_y = c->needD[level][1];
-            }
-            if ((err = mipGenerateLevel(c->diffuse, level, q, r))) break;
-        }
-    }
+    int err = pbrRegeneratePyramid(c, c->diffuse, qD, c->banded ? c->needD : nullptr, rects, n);
     traceEnd(c);
     // depth: replicateBordersTouching(area) (graphics.d:1406-1408) is clamp-to-edge addressing on the device
     traceBegin(c, "depth mipmap");
-    if (fused && !err) {
-        int q[kMaxDepthLevels];
-        const int nl = (int)c->depth->levels.size() - 1;
-        for (int level = 1; level <= nl; ++level) q[level - 1] = level >= 3 ? B2_QUALITY_CUBIC : B2_QUALITY_BOX;
-        err = b2mip_generate_levels(c->depth, 1, nl, q, rects[0], nullptr);
-    }
-    for (int level = 1; !fused && level < (int)c->depth->levels.size() && !err; ++level) {
-        int q = level >= 3 ? B2_QUALITY_CUBIC : B2_QUALITY_BOX;  // graphics.d:1414
-        for (auto& area : s1) {
-            const DevLevel& Pv = c->depth->levels[level - 1];
-            area = impactOnNextLevel(q, area, Pv.w, Pv.h);
-            b2_box2i r = area;
-            if (c->banded) {
-                if (r.min_y < c->needZ[level][0]) r.min_y = c->needZ[level][0];
-                if (r.max_y > c->needZ[level][1]) r.max_y = c->needZ[level][1];
-            }
-            if ((err = mipGenerateLevel(c->depth, level, q, r))) break;
-        }
-    }
+    if (!err) err = pbrRegeneratePyramid(c, c->depth, qZ, c->banded ? c->needZ : nullptr, rects, n);
     traceEnd(c);
     if (fork) {
         c->depth->stream = c->stream;
@@ -1740,3 +1757,5 @@ int b2pbr_trace_json(b2pbr* c, char* buf, size_t cap, size_t* needed) {
 uint64_t b2pbr_kernel_launches(const b2pbr* c) { return c ? c->launches : 0; }
 
 }  // extern "C"
+
+#include "band_exchange.inl"

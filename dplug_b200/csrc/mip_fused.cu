@@ -21,6 +21,7 @@ constexpr int FUSED_THREADS = 256;
 struct Iv { int a, b; };   // half-open interval of texel indices
 __device__ __forceinline__ bool inIv(Iv r, int v) { return v >= r.a && v < r.b; }
 __device__ __forceinline__ Iv ivUnion(Iv p, Iv q) { return Iv{min(p.a, q.a), max(p.b, q.b)}; }
+__device__ __forceinline__ Iv ivClip(Iv r, int lo, int hi) { const int a = max(r.a, lo), b = min(r.b, hi); return Iv{a, max(a, b)}; }
 // texels of the finer level owned by the CTA that owns `up` of the coarser one: the 2x2 children, plus the odd last
 // column / row of the finer level (it has no parent, mipmap.d:119-125) for the tile touching the edge
 __device__ __forceinline__ Iv ivChildren(Iv up, int dimUp, int dimDown) { return Iv{2 * up.a, up.b == dimUp ? dimDown : 2 * up.b}; }
@@ -331,10 +332,20 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_mip_fused(const __grid_con
         compX[k - 1] = ivUnion(ownX[k - 1], ivNeed(A.q[k - 1], compX[k], A.lv[k - 1].w));
         compY[k - 1] = ivUnion(ownY[k - 1], ivNeed(A.q[k - 1], compY[k], A.lv[k - 1].h));
     }
+    // Row bands (multi-GPU) store only a window of rows of every level: nothing outside it is read
+    // or held.  Every texel a band regenerates has its sources inside the band's windows (b2_band_need_rows), and the
+    // texels of a tile outside the update rectangles are only ever copied from the stored level, so clipping the
+    // regions to the stored rows changes nothing on an unbanded pyramid and keeps a band inside its allocation.
+#pragma unroll
+    for (int k = 1; k <= N; ++k) {
+        compY[k] = ivClip(compY[k], A.lv[k].y0, A.lv[k].y0 + A.lv[k].rows);
+        ownY[k] = ivClip(ownY[k], A.lv[k].y0, A.lv[k].y0 + A.lv[k].rows);
+    }
     constexpr int G = sizeof(T) == 4 ? 2 : 4;
     const Region<T> r1 = B2_REGION(T, buf1, compX[1].a & ~(G - 1), compY[1].a, B1W, B1H);
     if (STAGE0) {
-        const Iv sx = ivNeed(A.q[0], compX[1], A.lv[0].w), sy = ivNeed(A.q[0], compY[1], A.lv[0].h);
+        const Iv sx = ivNeed(A.q[0], compX[1], A.lv[0].w);
+        const Iv sy = ivClip(ivNeed(A.q[0], compY[1], A.lv[0].h), A.lv[0].y0, A.lv[0].y0 + A.lv[0].rows);
         const Region<T> r0 = B2_REGION(T, buf0, sx.a & ~1, sy.a, B0W, B0H);
         stageRegion<T>(A.lv[0], sx, sy, r0);
         __syncthreads();

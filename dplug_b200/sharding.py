@@ -1,10 +1,13 @@
-"""Multi-GPU sharding of the path: host-side planning only, no device work.
+"""Multi-GPU sharding of the path.
 
-* batch of plug-in UIs (BASELINE config 4): instances are independent -> round-robin blocks, no communication;
+* batch of plug-in UIs (BASELINE config 4): instances are independent -> contiguous blocks, no communication;
 * one large canvas (config 5): horizontal row bands; the only exchange is the level-0 halo rows (diffuse and
-  depth) between neighbouring bands, once per frame.  `halo_plan` derives the rows from the same arithmetic
-  the library uses (b2_band_need_rows), `exchange_halos` moves them with torch.distributed point-to-point
-  operations (NCCL over NVLink on GPUs, gloo in the CPU tests).
+  depth) between neighbouring bands, once per frame.  The exchange and the overlapped frame schedule live in the
+  library behind the C ABI (`b2band_*`, include/b2pbr.h; `BandGroup` below is its ctypes wrapper): NCCL send/recv
+  for one process per GPU, copy-engine peer copies for one process driving several GPUs.
+  The planning functions below (`halo_plan`, `own_and_halo_rects`, `interior_tile_rows`) restate the library's
+  planning arithmetic in Python; the tests check the two against each other, and `exchange_halos` is the same
+  exchange over torch.distributed (gloo) for the world-size-2 CPU test.
 """
 import ctypes as C
 from . import _lib
@@ -142,3 +145,72 @@ def interior_tile_rows(W, H, y0, y1, align=64):
             else:
                 b = cand[0]
     return a, b
+
+
+class BandGroup:
+    """ctypes wrapper of b2band (include/b2pbr.h): the halo exchange and the frame schedule of row bands.
+
+    BandGroup.nccl(band, rank, world, H, dist): one process per GPU; the NCCL unique id is created by rank 0 in the
+    library and broadcast over `dist` (any torch.distributed group; only 128 bytes of host data travel).
+    BandGroup.peers(bands): every band in this process (one thread drives several GPUs; copy-engine pushes)."""
+
+    def __init__(self, handle, keep):
+        self._h, self._keep, self._l = handle, keep, _lib.lib()
+
+    @staticmethod
+    def band_y(H, world, align=64):
+        return [band_rows(H, r, world, align)[0] for r in range(world)] + [band_rows(H, world - 1, world, align)[1]]
+
+    @classmethod
+    def nccl(cls, band, rank, world, H, dist=None, align=64):
+        l = _lib.lib()
+        ident = C.create_string_buffer(128)
+        if world > 1:
+            import torch
+            if rank == 0:
+                _lib.check(l.b2_band_nccl_unique_id(ident))
+            box = [bytes(ident.raw)]
+            dist.broadcast_object_list(box, src=0)
+            ident = C.create_string_buffer(box[0], 128)
+        ys = (C.c_int * (world + 1))(*cls.band_y(H, world, align))
+        h = C.c_void_p()
+        _lib.check(l.b2band_create_nccl(C.byref(h), band.handle, rank, world, ys, ident, None))
+        return cls(h, [band])
+
+    @classmethod
+    def peers(cls, bands):
+        l = _lib.lib()
+        arr = (C.c_void_p * len(bands))(*[b.handle for b in bands])
+        h = C.c_void_p()
+        _lib.check(l.b2band_create_peers(C.byref(h), arr, len(bands)))
+        return cls(h, list(bands))
+
+    def close(self):
+        if self._h:
+            self._l.b2band_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def exchangeBegin(self): _lib.check(self._l.b2band_exchange_begin(self._h))
+    def exchangeEnd(self): _lib.check(self._l.b2band_exchange_end(self._h))
+    def compositeFrame(self): _lib.check(self._l.b2band_composite_frame(self._h))
+    def sync(self): _lib.check(self._l.b2band_sync(self._h))
+    def haloBytesPerFrame(self): return int(self._l.b2band_halo_bytes_per_frame(self._h))
+
+    def info(self, index=0):
+        v = [C.c_int() for _ in range(5)]
+        _lib.check(self._l.b2band_info(self._h, index, *[C.byref(x) for x in v]))
+        return dict(zip(("rank", "interior_lo", "interior_hi", "n_sends", "n_recvs"), (x.value for x in v)))
+
+
+def band_plan(W, H, y0, y1, align=64):
+    """the library's planning of one band: (halo rectangles, (interior_lo, interior_hi))"""
+    rects = (_lib.box2i * 2)()
+    n, lo, hi = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(_lib.lib().b2_band_plan(W, H, y0, y1, align, rects, C.byref(n), C.byref(lo), C.byref(hi)))
+    return [rects[k].astuple() for k in range(n.value)], (lo.value, hi.value)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B2PBR_ABI_VERSION 1
+#define B2PBR_ABI_VERSION 2
 
 /* box2i — math/dplug/math/box.d:29-30,51-55 ({min.x,min.y,max.x,max.y}, 4 x int32) */
 typedef struct { int min_x, min_y, max_x, max_y; } b2_box2i;
@@ -215,6 +215,43 @@ int b2pbr_download_swizzled(b2pbr*, int pixel_format, void* host, size_t host_pi
 /* the same "need" rows as pure host arithmetic (no device, no object): used to plan the halo exchange */
 int b2_band_need_rows(int W, int H, int y0, int y1, int map, int level, int* need_lo, int* need_hi);
 int b2pbr_band_rows(const b2pbr*, int map, int level, int* stored_lo, int* stored_hi, int* need_lo, int* need_hi);
+/* ------------------------------------------------------------------------------------------
+ * b2band — multi-GPU row bands of one canvas (BASELINE config 5): the per-frame exchange of the
+ * level-0 halo rows between neighbouring bands and the overlapped frame schedule.  The caller of
+ * GUIGraphics.compositeGUI (gui/dplug/gui/graphics.d:1338-1349) drives one band object (b2pbr_create_band) per GPU.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b2band b2band;
+enum { B2_BAND_TRANSPORT_NCCL = 0, B2_BAND_TRANSPORT_PEERS = 1 };
+/* rows [y0, y1) of band `rank` of `nranks`: equal shares of the `align`-row GUI tiles (graphics.d:59-60: 64) */
+int b2_band_rows(int H, int nranks, int rank, int align, int* y0, int* y1);
+/* planning (host arithmetic only): the level-0 halo rectangles of band [y0, y1) (0..2: above / below) and the rows
+ * [interior_lo, interior_hi) of whole tiles that can be composited before the halo rows have arrived */
+int b2_band_plan(int W, int H, int y0, int y1, int align, b2_box2i halo_rects[2], int* n_halo, int* interior_lo, int* interior_hi);
+/* NCCL transport, one process per GPU.  libnccl.so.2 is loaded at run time (dlopen; B2_NCCL_LIB overrides the name).
+ * b2_band_nccl_unique_id = ncclGetUniqueId: rank 0 calls it and hands the 128 bytes to the other ranks over any host
+ * channel.  b2band_create_nccl is collective (ncclCommInitRank) unless `nccl_comm` — an ncclComm_t the caller owns,
+ * whose ranks are the band indices — is given.  band_y[nranks + 1] = the band boundaries every rank agrees on. */
+int b2_band_nccl_unique_id(void* id128);
+int b2band_create_nccl(b2band** out, b2pbr* band, int rank, int nranks, const int* band_y, const void* id128, void* nccl_comm);
+/* PEERS transport, all bands in this process (bands[r] = band r, adjacent in rank order, any mix of devices): halo rows
+ * are pushed GPU to GPU with cudaMemcpyPeerAsync on the copy engines; peer access is enabled where the devices differ. */
+int b2band_create_peers(b2band** out, b2pbr* const* bands, int nranks);
+void b2band_destroy(b2band*);
+/* Starts this frame's halo exchange on the bands' exchange streams, ordered after everything enqueued so far on each
+ * band's stream (its level-0 uploads / widget draws); returns without waiting.  Only halo rows are written. */
+int b2band_exchange_begin(b2band*);
+/* Makes each band's stream wait for the exchange (no host synchronisation).  Level 0 of a band may be modified again
+ * only after this (the neighbours read the band's own rows). */
+int b2band_exchange_end(b2band*);
+/* One frame of every local band = GUIGraphics.regenerateMipmaps + compositeGUI over the band's rows, with the exchange
+ * hidden behind the work that does not depend on it: exchange_begin; mips of the own rows; interior tiles; on a second
+ * stream, once the rows are there, the mips that depend on halo rows; boundary tiles.  Bit-identical to the unbanded
+ * frame.  Asynchronous: enqueue-only, results are in b2pbr_output / b2pbr_download of each band. */
+int b2band_composite_frame(b2band*);
+int b2band_sync(b2band*);
+uint64_t b2band_halo_bytes_per_frame(const b2band*);     /* level-0 bytes the local bands receive per frame */
+int b2band_info(const b2band*, int local_index, int* rank, int* interior_lo, int* interior_hi, int* n_sends, int* n_recvs);
+
 /* CUDA graph of one frame's device work: between _begin and _end, calls on this object (regenerate_mipmaps,
  * composite_tile on device maps, composite_raw) are recorded instead of executed; _launch replays them on the
  * object's stream.  Valid while sizes, rectangle lists and parameters stay the same (pixel contents may change).

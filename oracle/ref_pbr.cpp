@@ -8,7 +8,11 @@
 #include "ref_pbr.hpp"
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
+#include <utility>
+#include <vector>
 
 namespace b2ref {
 
@@ -489,24 +493,76 @@ void PBRCompositor::compositeOneTile(int t, box2i area, ImageRef<RGBA>& wfb, Mip
     if (m & (1u << PASS_CLAMP)) passClamp(t, area, wfb);
 }
 
+// ThreadPool.parallelFor (core/dplug/core/thread.d:431-520): a PERSISTENT pool — the reference creates its workers once
+// (thread.d:392-405) and wakes them per call; work items are handed out through a shared atomic counter
+// (thread.d:586-601).  One pool per thread count, created on first use and kept for the life of the process.
+namespace {
+class Pool {
+public:
+    explicit Pool(int n) : n_(n) {
+        for (int t = 0; t < n; ++t) workers_.emplace_back([this, t] { run(t); });
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; ++gen_; }
+        wake_.notify_all();
+        for (auto& w : workers_) w.join();
+    }
+    void parallelFor(int count, void (*fn)(int, int, void*), void* user) {
+        std::unique_lock<std::mutex> g(m_);
+        fn_ = fn; user_ = user; count_ = count; next_.store(0); pending_ = n_; ++gen_;
+        wake_.notify_all();
+        done_.wait(g, [this] { return pending_ == 0; });
+    }
+private:
+    void run(int t) {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> g(m_);
+                wake_.wait(g, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            for (;;) {
+                const int i = next_.fetch_add(1);
+                if (i >= count_) break;
+                fn_(i, t, user_);
+            }
+            std::lock_guard<std::mutex> g(m_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    int n_;
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable wake_, done_;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+    void (*fn_)(int, int, void*) = nullptr;
+    void* user_ = nullptr;
+    int count_ = 0, pending_ = 0;
+    std::atomic<int> next_{0};
+};
+std::mutex g_poolsLock;
+std::vector<std::pair<int, Pool*>> g_pools;   // leaked on purpose: workers must outlive static destruction order
+Pool* poolFor(int n) {
+    std::lock_guard<std::mutex> g(g_poolsLock);
+    for (auto& p : g_pools)
+        if (p.first == n) return p.second;
+    g_pools.emplace_back(n, new Pool(n));
+    return g_pools.back().second;
+}
+std::mutex g_callLock;   // one parallelFor at a time per process (the reference's pool is not re-entrant either)
+}  // namespace
+
 void parallelFor(int numThreads, int count, void (*fn)(int, int, void*), void* user) {
     if (count <= 0) return;
     if (count == 1 || numThreads <= 1) {  // thread.d:484-489: inline on threadIndex 0
         for (int i = 0; i < count; ++i) fn(i, 0, user);
         return;
     }
-    std::atomic<int> next(0);
-    std::vector<std::thread> pool;
-    int n = numThreads < count ? numThreads : count;
-    for (int t = 0; t < n; ++t)
-        pool.emplace_back([&, t]() {
-            for (;;) {
-                int i = next.fetch_add(1);
-                if (i >= count) break;
-                fn(i, t, user);
-            }
-        });
-    for (auto& th : pool) th.join();
+    std::lock_guard<std::mutex> g(g_callLock);
+    poolFor(numThreads)->parallelFor(count, fn, user);
 }
 
 void PBRCompositor::compositeTile(ImageRef<RGBA> wfb, const box2i* areas, int numAreas, Mipmap<RGBA>& diffuseMap,

@@ -248,6 +248,13 @@ class Graphics:
         self.materialMap.upload(0, material)
         self.depthMap.upload(0, depth)
 
+    def setInputRows(self, diffuse, material, depth, row0=0):
+        """level-0 rows [row0, row0 + n) only (bounded samples of large canvases)"""
+        n = diffuse.shape[0]
+        self.diffuseMap.level(0)[row0:row0 + n] = diffuse
+        self.materialMap.level(0)[row0:row0 + n] = material
+        self.depthMap.level(0)[row0:row0 + n] = depth
+
     def regenerateMipmaps(self, rects):
         assert self.l.b2ref_gfx_regenerate_mipmaps(self.g, boxes(rects), len(rects)) == 0
 

@@ -243,7 +243,7 @@ def test_profiler_trace(b2):
     ev = json.loads(comp.traceJSON())
     names = [e["name"] for e in ev]
     assert "PBR compositeTile" in names and "diffuse mipmap" in names and all(e["ph"] == "X" and e["dur"] >= 0 for e in ev)
-    assert comp.kernelLaunches() >= 10
+    assert 5 <= comp.kernelLaunches() <= 8     # NULL update list: the tile list is coalesced, 2 + 2 fused mip launches + lighting
 
 
 def test_host_call_full_frame_pipelined(b2, oracle):

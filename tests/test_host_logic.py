@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "b2pbr.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(b2(?:pbr|mip|layer)?_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(b2(?:pbr|mip|layer|band)?_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol(b2):
@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(b2):
     assert not missing, missing
     # and the Python binding table covers exactly the header
     assert sorted(_lib.SIGNATURES) == names
-    assert _lib.lib().b2_abi_version() == 1
+    assert _lib.lib().b2_abi_version() == 2
 
 
 def test_no_cpu_fallback(b2):

@@ -198,3 +198,124 @@ def test_banded_composite_equals_unbanded(b2, mode, world):
         for l in range(1, 6):
             _, _, lo, hi = c2.bandRows(sh.DIFFUSE, l)
             assert np.array_equal(c2.diffuseMap.downloadRows(l, lo, hi), ref.diffuseMap.download(l)[lo:hi]), ("overlapped", l)
+
+
+@pytest.mark.parametrize("W,H,world", [(16384, 16384, 8), (16384, 16384, 2), (3840, 2160, 4), (384, 960, 3), (256, 1024, 2), (1000, 777, 2)])
+def test_library_band_plan_matches_python_planning(b2, W, H, world):
+    """b2_band_rows / b2_band_plan (what b2band_composite_frame schedules by) against the Python restatement."""
+    import ctypes as C
+    from dplug_b200 import sharding as sh, _lib
+    for r in range(world):
+        y0, y1 = C.c_int(), C.c_int()
+        assert _lib.lib().b2_band_rows(H, world, r, 64, C.byref(y0), C.byref(y1)) == 0
+        assert (y0.value, y1.value) == sh.band_rows(H, r, world)
+        if y1.value <= y0.value:
+            continue
+        halos, interior = sh.band_plan(W, H, y0.value, y1.value)
+        assert halos == sh.own_and_halo_rects(W, H, y0.value, y1.value)[1]
+        assert interior == sh.interior_tile_rows(W, H, y0.value, y1.value)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_band_group_peers_frames_equal_unbanded(b2, world):
+    """b2band (PEERS transport, every band on device 0 here; on a multi-GPU box spread over the devices): several
+    frames with CHANGING content through b2band_composite_frame; every band's rows equal the unbanded frame bit for
+    bit.  Halos start poisoned, so a frame that reads a row before it arrived (or a stale row of the previous frame)
+    fails."""
+    from dplug_b200 import sharding as sh, synth, _lib
+    W, H = 384, 960
+    ndev = _lib.lib().b2_device_count()
+    sky = synth.skybox(128, 96)
+    ref = b2.PBRCompositor(0); ref.resizeBuffers(W, H); ref.setSkybox(sky)
+    bands = []
+    for r in range(world):
+        y0, y1 = sh.band_rows(H, r, world)
+        c = b2.PBRCompositor(r % ndev, band=(y0, y1)); c.resizeBuffers(W, H); c.setSkybox(sky)
+        for which in (sh.DIFFUSE, sh.DEPTH):
+            slo, shi, lo, hi = c.bandRows(which, 0)
+            elem = 4 if which == sh.DIFFUSE else 2
+            poison = np.full((shi - slo, W, 4) if elem == 4 else (shi - slo, W), 0xAB, dtype=np.uint8 if elem == 4 else np.uint16)
+            c.map(which).uploadRows(0, poison, slo)
+        bands.append((c, y0, y1))
+    grp = sh.BandGroup.peers([c for c, _, _ in bands])
+    assert grp.haloBytesPerFrame() > 0 and grp.info(0)["n_recvs"] == 2 and grp.info(1)["n_sends"] == (2 if world == 2 else 4)
+    for frame in range(3):
+        d, m, z = synth.frame(W, H, synth.SEED + 17 * frame)
+        ref.diffuseMap.upload(0, d); ref.materialMap.upload(0, m); ref.depthMap.upload(0, z)
+        ref.regenerateMipmaps([(0, 0, W, H)]); ref.compositeGUI([(0, 0, W, H)])
+        want = ref.download()
+        for c, y0, y1 in bands:       # every band uploads ONLY its own rows
+            c.diffuseMap.uploadRows(0, d[y0:y1], y0); c.materialMap.uploadRows(0, m[y0:y1], y0); c.depthMap.uploadRows(0, z[y0:y1], y0)
+        grp.compositeFrame()
+        grp.sync()
+        for c, y0, y1 in bands:
+            assert np.array_equal(c.downloadRows(y0, y1), want[y0:y1]), (frame, y0, y1)
+            for l in range(1, 6):
+                _, _, lo, hi = c.bandRows(sh.DIFFUSE, l)
+                assert np.array_equal(c.diffuseMap.downloadRows(l, lo, hi), ref.diffuseMap.download(l)[lo:hi]), (frame, l)
+    # the exchange alone (a host that schedules the frame itself)
+    d, m, z = synth.frame(W, H, synth.SEED + 99)
+    for c, y0, y1 in bands:
+        c.diffuseMap.uploadRows(0, d[y0:y1], y0); c.depthMap.uploadRows(0, z[y0:y1], y0)
+    grp.exchangeBegin(); grp.exchangeEnd(); grp.sync()
+    for c, y0, y1 in bands:
+        _, _, lo, hi = c.bandRows(sh.DIFFUSE, 0)
+        assert np.array_equal(c.diffuseMap.downloadRows(0, lo, hi), d[lo:hi])
+        _, _, lo, hi = c.bandRows(sh.DEPTH, 0)
+        assert np.array_equal(c.depthMap.downloadRows(0, lo, hi), z[lo:hi])
+    grp.close()
+
+
+_NCCL_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+import dplug_b200 as b2
+from dplug_b200 import sharding as sh, synth
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("gloo", rank=rank, world_size=world)      # host channel for the 128-byte NCCL id only
+W, H = 640, 1536
+sky = synth.skybox(128, 96)
+y0, y1 = sh.band_rows(H, rank, world)
+c = b2.PBRCompositor(rank, band=(y0, y1)); c.resizeBuffers(W, H); c.setSkybox(sky)
+ref = b2.PBRCompositor(rank); ref.resizeBuffers(W, H); ref.setSkybox(sky)
+grp = sh.BandGroup.nccl(c, rank, world, H, dist)
+ok = True
+for frame in range(4):
+    d, m, z = synth.frame(W, H, synth.SEED + 31 * frame)
+    ref.diffuseMap.upload(0, d); ref.materialMap.upload(0, m); ref.depthMap.upload(0, z)
+    ref.regenerateMipmaps([(0, 0, W, H)]); ref.compositeGUI([(0, 0, W, H)])
+    want = ref.download()
+    c.diffuseMap.uploadRows(0, d[y0:y1], y0); c.materialMap.uploadRows(0, m[y0:y1], y0); c.depthMap.uploadRows(0, z[y0:y1], y0)
+    grp.compositeFrame(); grp.sync()
+    ok = ok and np.array_equal(c.downloadRows(y0, y1), want[y0:y1])
+t = torch.tensor([1 if ok else 0]); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("RESULT", int(t.item()), grp.haloBytesPerFrame())
+grp.close()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.gpu
+def test_band_group_nccl_world2(b2, tmp_path):
+    """Two processes, one GPU each, halo rows over NCCL (ncclSend / ncclRecv inside the library): four frames with
+    changing content, each band equal to the unbanded frame.  Needs two GPUs."""
+    from dplug_b200 import _lib
+    if _lib.lib().b2_device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    script = tmp_path / "nccl_worker.py"
+    script.write_text(_NCCL_WORKER % {"root": ROOT})
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    line = [l for l in outs[0][0].splitlines() if l.startswith("RESULT")][0].split()
+    assert line[1] == "1" and int(line[2]) > 0
