@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "composited Mpix/s (full PBR frame)"
+_OUT = sys.stdout
 WORKLOADS = {
     # name: (W, H, description)
     "c1": (620, 330, "C1 examples/distort default size 620x330, full-frame composite"),
@@ -201,7 +202,7 @@ def run_reference(args, workload):
            "config": config_for(workload, args.gpus),
            "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample, "note": CPU_NOTE},
            "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_OUT, flush=True)
 
 
 def cpu_baseline(W, H, budget_s=20.0):
@@ -675,7 +676,7 @@ def run_default_single(args):
         out["extra"] = extra
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(W, H)
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_OUT, flush=True)
 
 
 def run_default_multi(args):
@@ -697,7 +698,7 @@ def run_default_multi(args):
     dist.all_reduce(halo)
     if rank == 0:
         if not r["parity"]["bands_equal_unbanded_frame"]:
-            print(json.dumps({"error": "C5 parity failed: a band's output differs from the unbanded frame", "parity": r["parity"]}), flush=True)
+            print(json.dumps({"error": "C5 parity failed: a band's output differs from the unbanded frame", "parity": r["parity"]}), file=_OUT, flush=True)
             dist.destroy_process_group()
             sys.exit(1)
         peak, peak_src = _peak()
@@ -721,7 +722,7 @@ def run_default_multi(args):
             "e2e": r.get("e2e"), "secondary": sec,
             "gpu_launches": r["launches"], "clocks": r.get("clocks"),
         }
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=_OUT, flush=True)
     dist.destroy_process_group()
 
 
@@ -742,7 +743,7 @@ def run_workload(args):
                           "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config_for("c3", 1),
                           "roofline": {"bound": "hbm", "kernel": "mip chain", "achieved": head["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": head["frac"],
                                        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": r["algorithmic_bytes_per_step"]},
-                          "variants": r, "gpu_launches": head["gpu_launches"]}), flush=True)
+                          "variants": r, "gpu_launches": head["gpu_launches"]}), file=_OUT, flush=True)
         return
     world, rank, dist = _dist_init(local)
     if wl == "c5":
@@ -751,7 +752,7 @@ def run_workload(args):
             print(json.dumps({"metric": METRIC, "value": W * H / (r["ms_per_step"] * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
                               "warmup": max(3, args.warmup), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_for("c5", world), "result": r,
-                              "gpu_launches": r["launches"], "clocks": r.get("clocks")}), flush=True)
+                              "gpu_launches": r["launches"], "clocks": r.get("clocks")}), file=_OUT, flush=True)
     else:
         batch = wl == "c4"
         r = frame_bench(local, W, H, args.instances, args.steps, args.warmup, graph=bool(args.graph), batch=batch, batch_streams=args.batch_streams,
@@ -768,12 +769,16 @@ def run_workload(args):
                    "e2e": r.get("e2e"), "gpu_launches": r["launches"], "clocks": r.get("clocks")}
             if world == 1 and not args.no_cpu_baseline and wl in ("c1", "c2"):
                 out["cpu_baseline"] = cpu_baseline(W, H)
-            print(json.dumps(out), flush=True)
+            print(json.dumps(out), file=_OUT, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries the ONE JSON line and nothing else: libraries that print to fd 1 (NCCL's version banner) go to stderr
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

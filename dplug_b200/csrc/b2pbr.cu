@@ -629,6 +629,8 @@ struct b2pbr {
     uint64_t launchesAtCapture = 0;
     bool capturing = false;
     cudaStream_t sAux = nullptr;                  // the depth pyramid is regenerated next to the diffuse one
+    cudaStream_t sAuxHi = nullptr;                // ... and on this high-priority twin when the caller's stream is a priority stream (b2band's halo pass)
+    bool useAuxHi = false;
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     std::vector<cudaEvent_t> pipeEvents;
     uint8_t* dlStaging = nullptr; size_t dlStagingBytes = 0;   // linear device buffer of b2pbr_download
@@ -994,6 +996,7 @@ void b2pbr_destroy(b2pbr* c) {
     if (c->boxCopied) cudaEventDestroy(c->boxCopied);
     for (auto g : c->graphs) if (g) cudaGraphExecDestroy(g);
     if (c->sAux) cudaStreamDestroy(c->sAux);
+    if (c->sAuxHi) cudaStreamDestroy(c->sAuxHi);
     if (c->evFork) cudaEventDestroy(c->evFork);
     if (c->evJoin) cudaEventDestroy(c->evJoin);
     if (c->sIn) cudaStreamDestroy(c->sIn);
@@ -1172,10 +1175,19 @@ int b2pbr_regenerate_mipmaps(b2pbr* c, const b2_box2i* rects, int n) {
     // graphics.d:1369-1370): the depth chain runs on a second stream beside the diffuse chain and joins before
     // anything else is enqueued on the compositor's stream.
     const bool fork = !c->profile;
+    cudaStream_t aux = c->sAux;
+    if (fork && c->useAuxHi) {
+        if (!c->sAuxHi) {
+            int least = 0, greatest = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            CU(cudaStreamCreateWithPriority(&c->sAuxHi, cudaStreamNonBlocking, greatest));
+        }
+        aux = c->sAuxHi;
+    }
     if (fork) {
         CU(cudaEventRecord(c->evFork, c->stream));
-        CU(cudaStreamWaitEvent(c->sAux, c->evFork, 0));
-        c->depth->stream = c->sAux;
+        CU(cudaStreamWaitEvent(aux, c->evFork, 0));
+        c->depth->stream = aux;
     }
     int qD[kMaxDiffuseLevels], qZ[kMaxDepthLevels];
     for (int level = 1; level < kMaxDiffuseLevels; ++level) qD[level - 1] = level == 1 ? B2_QUALITY_BOX_ALPHACOV_PREMUL : B2_QUALITY_CUBIC;  // graphics.d:1380-1384
@@ -1189,7 +1201,7 @@ int b2pbr_regenerate_mipmaps(b2pbr* c, const b2_box2i* rects, int n) {
     traceEnd(c);
     if (fork) {
         c->depth->stream = c->stream;
-        CU(cudaEventRecord(c->evJoin, c->sAux));
+        CU(cudaEventRecord(c->evJoin, aux));
         CU(cudaStreamWaitEvent(c->stream, c->evJoin, 0));
     }
     if (err) return err;

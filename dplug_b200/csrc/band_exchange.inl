@@ -141,6 +141,9 @@ struct b2band {
         std::vector<HaloCopy> sends, recvs;
         std::vector<b2_box2i> interior, boundary, all;
         bool begun = false;
+        // B2_BAND_DEBUG: per-phase device times (events with timing), accumulated over the frames and printed by b2band_destroy
+        cudaEvent_t t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // frame start, own mips, interior, arrival, halo mips, boundary
+        double acc[5] = {0, 0, 0, 0, 0}; int frames = 0; bool timed = false;
     };
     std::vector<Local> locals;         // NCCL: the one band of this process; PEERS: every band, index = rank
     NcclComm comm = nullptr; bool ownComm = false;
@@ -206,9 +209,17 @@ int bandSetupLocal(b2band* g, b2band::Local& L) {
     for (const b2_box2i& e : edges)
         if (e.max_y > e.min_y) tileAreas(&e, 1, c->tileW, c->tileH, L.boundary);
     CU(cudaSetDevice(c->device));
-    CU(cudaStreamCreateWithFlags(&L.xs, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking));
+    // The transfers and the halo pass are short and everything after them waits for them, while the band's own stream
+    // is busy with a lighting launch of thousands of CTAs: on high-priority streams their CTAs are dispatched as soon as
+    // an SM slot frees up instead of after the last CTA of that launch (measured at 2 GPUs: the halo mips otherwise
+    // start 3.2 ms after the rows arrived, i.e. when the interior tiles are done).
+    int least = 0, greatest = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CU(cudaStreamCreateWithPriority(&L.xs, cudaStreamNonBlocking, greatest));
+    CU(cudaStreamCreateWithPriority(&L.side, cudaStreamNonBlocking, greatest));
     for (cudaEvent_t* e : {&L.evReady, &L.evX, &L.evOwn, &L.evHalo, &L.evDone}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    if (getenv("B2_BAND_DEBUG"))
+        for (cudaEvent_t& e : L.t) CU(cudaEventCreate(&e));
     return B2_OK;
 }
 
@@ -216,6 +227,15 @@ int bandSetupLocal(b2band* g, b2band::Local& L) {
 int bandBegin(b2band* g, b2band::Local& L, bool composite) {
     b2pbr* c = L.c;
     CU(cudaSetDevice(c->device));
+    if (L.t[0] && composite) {
+        if (L.timed && cudaEventQuery(L.t[5]) == cudaSuccess && cudaEventQuery(L.t[4]) == cudaSuccess) {
+            const int a[5] = {0, 1, 0, 3, 0}, b[5] = {1, 2, 3, 4, 5};   // own mips, interior tiles, arrival since start, halo mips, whole frame
+            for (int k = 0; k < 5; ++k) { float ms = 0; cudaEventElapsedTime(&ms, L.t[a[k]], L.t[b[k]]); L.acc[k] += ms; }
+            L.frames++;
+        }
+        cudaGetLastError();
+        CU(cudaEventRecord(L.t[0], c->stream));
+    }
     // the transfers read this band's own rows: after everything the caller enqueued on the band's stream (its uploads)
     CU(cudaEventRecord(L.evReady, c->stream));
     CU(cudaStreamWaitEvent(L.xs, L.evReady, 0));
@@ -251,13 +271,16 @@ int bandBegin(b2band* g, b2band::Local& L, bool composite) {
         }
     }
     CU(cudaEventRecord(L.evX, L.xs));
+    if (L.t[0] && composite) CU(cudaEventRecord(L.t[3], L.xs));
     L.begun = true;
     if (!composite) return B2_OK;
     if (L.plan.nHalo == 0) return B2_OK;   // a single band: everything happens in phase B
     if (int rc = b2pbr_regenerate_mipmaps(c, &L.plan.own, 1)) return rc;
     CU(cudaEventRecord(L.evOwn, c->stream));
+    if (L.t[0]) CU(cudaEventRecord(L.t[1], c->stream));
     if (!L.interior.empty())
         if (int rc = pbrComposite(c, L.interior.data(), (int)L.interior.size(), nullptr, nullptr, nullptr)) return rc;
+    if (L.t[0]) CU(cudaEventRecord(L.t[2], c->stream));
     return B2_OK;
 }
 
@@ -285,11 +308,16 @@ int bandFinish(b2band* g, b2band::Local& L, bool composite) {
     } else {
         CU(cudaStreamWaitEvent(L.side, L.evOwn, 0));
         if (int rc = bandWaitArrival(g, L, L.side)) return rc;
-        if (int rc = b2pbr_regenerate_mipmaps_on(c, L.plan.halo, L.plan.nHalo, L.side)) return rc;
+        c->useAuxHi = true;
+        const int rcHalo = b2pbr_regenerate_mipmaps_on(c, L.plan.halo, L.plan.nHalo, L.side);
+        c->useAuxHi = false;
+        if (rcHalo) return rcHalo;
         CU(cudaEventRecord(L.evHalo, L.side));
+        if (L.t[0]) CU(cudaEventRecord(L.t[4], L.side));
         CU(cudaStreamWaitEvent(c->stream, L.evHalo, 0));
         if (!L.boundary.empty())
             if (int rc = pbrComposite(c, L.boundary.data(), (int)L.boundary.size(), nullptr, nullptr, nullptr)) return rc;
+        if (L.t[0]) { CU(cudaEventRecord(L.t[5], c->stream)); L.timed = true; }
     }
     CU(cudaStreamWaitEvent(c->stream, L.evX, 0));       // this band's sends have left: its rows may change again
     CU(cudaEventRecord(L.evDone, c->stream));           // its halo rows may be overwritten by the next frame's transfers
@@ -400,6 +428,12 @@ void b2band_destroy(b2band* g) {
         if (L.xs) { cudaStreamSynchronize(L.xs); cudaStreamDestroy(L.xs); }
         if (L.side) { cudaStreamSynchronize(L.side); cudaStreamDestroy(L.side); }
         for (cudaEvent_t e : {L.evReady, L.evX, L.evOwn, L.evHalo, L.evDone})
+            if (e) cudaEventDestroy(e);
+        if (L.t[0] && L.frames > 0)
+            fprintf(stderr, "[b2band] rank %d rows [%d,%d) interior [%d,%d): per frame over %d frames: own mips %.3f ms, interior tiles %.3f ms, halo rows arrived at +%.3f ms, "
+                            "halo mips %.3f ms after that, frame %.3f ms\n", L.rank, L.c->bandY0, L.c->bandY1, L.plan.interiorLo, L.plan.interiorHi, L.frames,
+                    L.acc[0] / L.frames, L.acc[1] / L.frames, L.acc[2] / L.frames, L.acc[3] / L.frames, L.acc[4] / L.frames);
+        for (cudaEvent_t e : L.t)
             if (e) cudaEventDestroy(e);
     }
     if (g->ownComm && g->comm && ncclApi()) ncclApi()->CommDestroy(g->comm);
