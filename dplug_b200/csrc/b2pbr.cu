@@ -34,6 +34,7 @@ void launch_fill32(const DevLevel& win, uint32_t value, cudaStream_t s);
 void launch_pbr_exact(const PbrArgs& args, int gridBlocks, cudaStream_t stream);
 void launch_pbr_fast(const PbrArgs& args, cudaStream_t stream);
 int pbr_fast_strip_rows();
+void launch_pbr_tex(const PbrArgs& args, cudaStream_t stream);
 void launch_sample(const DevLevel* levels, int nLevels, int color, int kind, int n, const float* lvl, const float* x,
                    const float* y, float* out4, cudaStream_t stream);
 }  // namespace b2
@@ -69,6 +70,9 @@ struct b2mip {
     uint64_t launches = 0;
     uint8_t* staging = nullptr;     // linear device buffer for uploads whose host pitch differs from the level's
     size_t stagingBytes = 0;
+    // every level as a pitch-2D texture object over the same memory (linear filter, clamp addressing, unnormalised
+    // coordinates, normalised-float reads): the lighting kernel's bilinear samplers run on the texture units
+    std::vector<cudaTextureObject_t> tex;
 };
 
 // A pitched host<->device copy is executed row by row by the copy engine (measured: 2 MB of 2480-byte rows take 160 us
@@ -127,7 +131,7 @@ static int mipAllocate(b2mip* m, int maxLevel) {
             L.y0 = lo; L.rows = hi - lo;
         }
         offs[l] = total;
-        total += alignUp((size_t)L.pitch * (size_t)(L.rows > 0 ? L.rows : 1), 256);
+        total += alignUp((size_t)L.pitch * (size_t)(L.rows > 0 ? L.rows : 1), 512);   // 512 B: texture base alignment
         w >>= 1; h >>= 1;
     }
     if (total == 0) total = 256;
@@ -135,6 +139,27 @@ static int mipAllocate(b2mip* m, int maxLevel) {
     m->allocBytes = total;
     CU(cudaMemsetAsync(m->alloc, 0, total, m->stream));
     for (int l = 0; l < n; ++l) m->levels[l].base = m->alloc + offs[l];
+    m->tex.assign(n, 0);
+    for (int l = 0; l < n; ++l) {
+        const DevLevel& L = m->levels[l];
+        if (L.w <= 0 || L.rows <= 0) continue;
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypePitch2D;
+        rd.res.pitch2D.devPtr = L.base;
+        rd.res.pitch2D.desc = m->color == B2_COLOR_RGBA8 ? cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindUnsigned)
+                                                         : cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned);
+        rd.res.pitch2D.width = (size_t)L.w;
+        rd.res.pitch2D.height = (size_t)L.rows;
+        rd.res.pitch2D.pitchInBytes = (size_t)L.pitch;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 0;
+        CU(cudaCreateTextureObject(&m->tex[l], &rd, &td, nullptr));
+    }
     return B2_OK;
 }
 
@@ -152,7 +177,11 @@ static int mipCreate(b2mip** out, int device, int color, int maxLevel, int w, in
     if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) { delete m; return fail(B2_ERR_CUDA, "cudaStreamCreate failed"); }
     m->ownStream = true;
     int rc = mipAllocate(m, maxLevel);
-    if (rc != B2_OK) { if (m->alloc) cudaFree(m->alloc); cudaStreamDestroy(m->stream); delete m; return rc; }
+    if (rc != B2_OK) {
+        for (cudaTextureObject_t t : m->tex) if (t) cudaDestroyTextureObject(t);
+        if (m->alloc) cudaFree(m->alloc);
+        cudaStreamDestroy(m->stream); delete m; return rc;
+    }
     *out = m;
     return B2_OK;
 }
@@ -335,6 +364,7 @@ void b2mip_destroy(b2mip* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    for (cudaTextureObject_t t : m->tex) if (t) cudaDestroyTextureObject(t);
     if (m->alloc) cudaFree(m->alloc);
     if (m->staging) cudaFree(m->staging);
     if (m->ownStream && m->stream) cudaStreamDestroy(m->stream);
@@ -608,6 +638,8 @@ struct b2pbr {
     // rows [lo, hi) of every pyramid level this band has to hold valid data for (banded objects only)
     int needD[kMaxDiffuseLevels][2], needZ[kMaxDepthLevels][2];
     b2mip *diffuse = nullptr, *material = nullptr, *depth = nullptr, *sky = nullptr;
+    std::vector<cudaArray_t> skyArr;              // the skybox levels once more as CUDA arrays (texture gather needs them)
+    std::vector<cudaTextureObject_t> skyTex;
     DevLevel out{}; uint8_t* outAlloc = nullptr;
     DevLevel swz{}; uint8_t* swzAlloc = nullptr;
     DevLevel win{}; uint8_t* winAlloc = nullptr;     // device twin of the window buffer (_resizedBuffer, graphics.d:1146)
@@ -650,6 +682,12 @@ static void pbrInvalidateGraphs(b2pbr* c) {
     for (auto& g : c->graphs)
         if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     for (auto& wl : c->workLists) wl.pinned = false;
+}
+
+static void pbrFreeSkyTextures(b2pbr* c) {
+    for (cudaTextureObject_t t : c->skyTex) if (t) cudaDestroyTextureObject(t);
+    for (cudaArray_t a : c->skyArr) if (a) cudaFreeArray(a);
+    c->skyTex.clear(); c->skyArr.clear();
 }
 
 static void pbrConstants(b2pbr* c) {
@@ -817,13 +855,16 @@ static int pbrUploadBoxes(b2pbr* c, const b2_box2i* areas, int n, int kind) {
     std::vector<Box> work;
     if (kind == 0) work.assign((const Box*)areas, (const Box*)areas + n);
     else {
+        // kind 1 (k_pbr_fast): warp strips of 32 columns x R rows; kind 2 (k_pbr_tex): CTA boxes of 64 columns x 2R rows,
+        // whose four warps take the four 32 x R quadrants
         const int R0 = stripRowsFor(areas, n);
+        const int bw = kind == 2 ? 64 : 32;
         for (int k = 0; k < n; ++k) {
             const b2_box2i& a = areas[k];
-            const int R = stripRowsOfAreaAt(c, k, n, a, R0);
+            const int R = stripRowsOfAreaAt(c, k, n, a, R0) * (kind == 2 ? 2 : 1);
             for (int y = a.min_y; y < a.max_y; y += R)
-                for (int x = a.min_x; x < a.max_x; x += 32)
-                    work.push_back(Box{x, y, x + 32 < a.max_x ? x + 32 : a.max_x, y + R < a.max_y ? y + R : a.max_y});
+                for (int x = a.min_x; x < a.max_x; x += bw)
+                    work.push_back(Box{x, y, x + bw < a.max_x ? x + bw : a.max_x, y + R < a.max_y ? y + R : a.max_y});
         }
     }
     const int m = (int)work.size();
@@ -883,8 +924,8 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
     CU(cudaSetDevice(c->device));
     // the throughput kernel assumes full pyramids (diffuse levels 0..5, depth 0..4: any canvas >= 32x32);
     // smaller canvases are shaded by the exact kernel
-    const bool fast = c->mode == B2_MODE_FAST && (int)diffuse->levels.size() >= kMaxDiffuseLevels && (int)depth->levels.size() >= kMaxDepthLevels;
-    int rc = pbrUploadBoxes(c, areas, n, fast ? 1 : 0);
+    const bool fast = c->mode != B2_MODE_EXACT && (int)diffuse->levels.size() >= kMaxDiffuseLevels && (int)depth->levels.size() >= kMaxDepthLevels;
+    int rc = pbrUploadBoxes(c, areas, n, !fast ? 0 : (c->mode == B2_MODE_FAST ? 2 : 1));
     if (rc) return rc;
     if (usedFast) *usedFast = fast;
     if (c->nDeviceBoxes == 0) return B2_OK;
@@ -917,9 +958,17 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
         A.skyPixels = (float)(c->sky->W * c->sky->H);
         A.skyFX = (float)c->sky->W - 1.0f;
         A.skyFY = (float)c->sky->H - 1.0f;
+        for (int l = 0; l < A.nSky; ++l) {
+            A.texSky[l] = l < (int)c->skyTex.size() ? c->skyTex[l] : 0;
+            A.skyMaxX[l] = (float)(c->sky->levels[l].w - 1);
+            A.skyMaxY[l] = (float)(c->sky->levels[l].h - 1);
+        }
     }
+    for (int l = 0; l < A.nDiffuse; ++l) A.texD[l] = diffuse->tex[l];
+    for (int l = 0; l < A.nDepth; ++l) A.texZ[l] = depth->tex[l];
     traceBegin(c, "PBR compositeTile");
-    if (fast) launch_pbr_fast(A, c->stream);
+    if (fast && c->mode == B2_MODE_FAST) launch_pbr_tex(A, c->stream);
+    else if (fast) launch_pbr_fast(A, c->stream);
     else launch_pbr_exact(A, A.nBoxes, c->stream);
     c->launches++;
     traceEnd(c);
@@ -984,6 +1033,7 @@ void b2pbr_destroy(b2pbr* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     pbrFreeMaps(c);
+    pbrFreeSkyTextures(c);
     b2mip_destroy(c->sky);
     if (c->winAlloc) cudaFree(c->winAlloc);
     if (c->dLut) cudaFree(c->dLut);
@@ -1062,7 +1112,7 @@ int b2pbr_set_params(b2pbr* c, const b2pbr_params* p) {
     return B2_OK;
 }
 int b2pbr_set_mode(b2pbr* c, int mode) {
-    if (!c || (mode != B2_MODE_FAST && mode != B2_MODE_EXACT)) return fail(B2_ERR_INVALID, "set_mode: bad arguments");
+    if (!c || (mode != B2_MODE_FAST && mode != B2_MODE_EXACT && mode != B2_MODE_FAST_ROLLING)) return fail(B2_ERR_INVALID, "set_mode: bad arguments");
     if (mode != c->mode) pbrInvalidateGraphs(c);
     c->mode = mode;
     return B2_OK;
@@ -1078,6 +1128,7 @@ int b2pbr_set_skybox(b2pbr* c, const uint8_t* rgba, int w, int h, size_t pitch) 
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     pbrInvalidateGraphs(c);
+    pbrFreeSkyTextures(c);
     b2mip_destroy(c->sky);
     c->sky = nullptr;
     if (!rgba) return B2_OK;
@@ -1091,6 +1142,28 @@ int b2pbr_set_skybox(b2pbr* c, const uint8_t* rgba, int w, int h, size_t pitch) 
     CU(cudaStreamSynchronize(c->stream));  // the caller may free its image right after this call
     if ((rc = b2mip_generate_mipmaps(c->sky, B2_QUALITY_BOX))) return rc;  // legacypbr.d:869
     c->launches += c->sky->launches;
+    // every level once more as a CUDA array with the gather flag: the lighting kernel reads the 2 x 2 footprints of the
+    // trilinear sample with texture gather (exact texels; the filter weights stay in FP32 in the kernel)
+    const int nl = (int)c->sky->levels.size();
+    c->skyArr.assign(nl, nullptr); c->skyTex.assign(nl, 0);
+    for (int l = 0; l < nl; ++l) {
+        const DevLevel& L = c->sky->levels[l];
+        const cudaChannelFormatDesc fd = cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindUnsigned);
+        CU(cudaMallocArray(&c->skyArr[l], &fd, (size_t)L.w, (size_t)L.h, cudaArrayTextureGather));
+        CU(cudaMemcpy2DToArrayAsync(c->skyArr[l], 0, 0, L.base, (size_t)L.pitch, (size_t)L.w * 4, (size_t)L.h, cudaMemcpyDeviceToDevice, c->stream));
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = c->skyArr[l];
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 0;
+        CU(cudaCreateTextureObject(&c->skyTex[l], &rd, &td, nullptr));
+    }
+    CU(cudaStreamSynchronize(c->stream));
     return B2_OK;
 }
 
@@ -1389,8 +1462,9 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
     const int R0 = stripRowsFor(areas, n_areas);
     auto workItems = [&](int k, const b2_box2i& a, bool fast) {   // k = index in the sorted list that is uploaded
         if (!fast) return 1;
-        const int R = stripRowsOfAreaAt(c, k, n_areas, a, R0);
-        return ((boxH(a) + R - 1) / R) * ((boxW(a) + 31) / 32);
+        const bool boxes = c->mode == B2_MODE_FAST;               // k_pbr_tex: CTA boxes of 64 x 2R; k_pbr_fast: strips of 32 x R
+        const int R = stripRowsOfAreaAt(c, k, n_areas, a, R0) * (boxes ? 2 : 1), bw = boxes ? 64 : 32;
+        return ((boxH(a) + R - 1) / R) * ((boxW(a) + bw - 1) / bw);
     };
     // stage 1: every upload is enqueued up front, so the copy engine never waits for this thread (the host-side cost
     // of enqueueing a stage's kernels is comparable to the transfer time of the small last chunks)

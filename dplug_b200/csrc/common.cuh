@@ -65,6 +65,12 @@ struct PbrArgs {
     float shadowInvTotal;
     float invW, invH;
     float skyPixels, skyFX, skyFY;
+    // texture-unit path (pbr_tex.cu): every pyramid level is also a pitch-2D texture (linear filter, clamp, unnormalised
+    // coordinates, normalised-float reads); the skybox levels are CUDA arrays read with texture gather
+    cudaTextureObject_t texD[kMaxDiffuseLevels];   // diffuse levels (1..3 are sampled)
+    cudaTextureObject_t texZ[kMaxDepthLevels];     // depth levels (1..4 are sampled)
+    cudaTextureObject_t texSky[kMaxSkyLevels];
+    float skyMaxX[kMaxSkyLevels], skyMaxY[kMaxSkyLevels];   // w - 1, h - 1 of every skybox level
 };
 
 }  // namespace b2

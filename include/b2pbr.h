@@ -44,9 +44,11 @@ enum {
 };
 /* the maps GUIGraphics owns and lends to the compositor — gui/dplug/gui/graphics.d:117-122 */
 enum { B2_MAP_DIFFUSE = 0, B2_MAP_MATERIAL = 1, B2_MAP_DEPTH = 2 };
-/* lighting kernels: FAST = throughput kernel (FMA / MUFU, +-1 LSB contract); EXACT = the reference's IEEE operation
- * order, bit-identical to the CPU restatement (several times slower; the device-side yardstick) */
-enum { B2_MODE_FAST = 0, B2_MODE_EXACT = 1 };
+/* lighting kernels: FAST = throughput kernel (texture units for the mip samplers, FMA / MUFU; +-1 LSB contract);
+ * EXACT = the reference's IEEE operation order, bit-identical to the CPU restatement (several times slower; the
+ * device-side yardstick); FAST_ROLLING = round 1's throughput kernel (samplers in FP32 from shared-memory windows;
+ * kept for A/B measurements, same contract) */
+enum { B2_MODE_FAST = 0, B2_MODE_EXACT = 1, B2_MODE_FAST_ROLLING = 2 };
 /* window pixel orders for the fused post-composite swizzle — window/dplug/window/window.d WindowPixelFormat */
 enum { B2_PF_RGBA8 = 0, B2_PF_BGRA8 = 1, B2_PF_ARGB8 = 2 };
 
