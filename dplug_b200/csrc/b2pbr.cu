@@ -35,6 +35,8 @@ void launch_pbr_exact(const PbrArgs& args, int gridBlocks, cudaStream_t stream);
 void launch_pbr_fast(const PbrArgs& args, cudaStream_t stream);
 int pbr_fast_strip_rows();
 void launch_pbr_tex(const PbrArgs& args, cudaStream_t stream);
+void sky_atlas_layout(const DevLevel* levels, int n, int* ox, int* oy, int* aw, int* ah);
+void launch_sky_atlas(const DevLevel* levels, int n, const int* ox, const int* oy, int aw, int ah, uint32_t* out, cudaStream_t s);
 void launch_sample(const DevLevel* levels, int nLevels, int color, int kind, int n, const float* lvl, const float* x,
                    const float* y, float* out4, cudaStream_t stream);
 }  // namespace b2
@@ -638,8 +640,9 @@ struct b2pbr {
     // rows [lo, hi) of every pyramid level this band has to hold valid data for (banded objects only)
     int needD[kMaxDiffuseLevels][2], needZ[kMaxDepthLevels][2];
     b2mip *diffuse = nullptr, *material = nullptr, *depth = nullptr, *sky = nullptr;
-    std::vector<cudaArray_t> skyArr;              // the skybox levels once more as CUDA arrays (texture gather needs them)
-    std::vector<cudaTextureObject_t> skyTex;
+    cudaArray_t skyArr = nullptr;                 // every skybox level once more in one CUDA array (texture gather needs one)
+    cudaTextureObject_t skyTex = 0;
+    int skyOx[kMaxSkyLevels], skyOy[kMaxSkyLevels];   // atlas position of texel (0, 0) of each level
     DevLevel out{}; uint8_t* outAlloc = nullptr;
     DevLevel swz{}; uint8_t* swzAlloc = nullptr;
     DevLevel win{}; uint8_t* winAlloc = nullptr;     // device twin of the window buffer (_resizedBuffer, graphics.d:1146)
@@ -685,9 +688,9 @@ static void pbrInvalidateGraphs(b2pbr* c) {
 }
 
 static void pbrFreeSkyTextures(b2pbr* c) {
-    for (cudaTextureObject_t t : c->skyTex) if (t) cudaDestroyTextureObject(t);
-    for (cudaArray_t a : c->skyArr) if (a) cudaFreeArray(a);
-    c->skyTex.clear(); c->skyArr.clear();
+    if (c->skyTex) cudaDestroyTextureObject(c->skyTex);
+    if (c->skyArr) cudaFreeArray(c->skyArr);
+    c->skyTex = 0; c->skyArr = nullptr;
 }
 
 static void pbrConstants(b2pbr* c) {
@@ -958,10 +961,12 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
         A.skyPixels = (float)(c->sky->W * c->sky->H);
         A.skyFX = (float)c->sky->W - 1.0f;
         A.skyFY = (float)c->sky->H - 1.0f;
+        A.texSky = c->skyTex;
         for (int l = 0; l < A.nSky; ++l) {
-            A.texSky[l] = l < (int)c->skyTex.size() ? c->skyTex[l] : 0;
             A.skyMaxX[l] = (float)(c->sky->levels[l].w - 1);
             A.skyMaxY[l] = (float)(c->sky->levels[l].h - 1);
+            A.skyOx[l] = (float)c->skyOx[l];
+            A.skyOy[l] = (float)c->skyOy[l];
         }
     }
     for (int l = 0; l < A.nDiffuse; ++l) A.texD[l] = diffuse->tex[l];
@@ -1142,26 +1147,34 @@ int b2pbr_set_skybox(b2pbr* c, const uint8_t* rgba, int w, int h, size_t pitch) 
     CU(cudaStreamSynchronize(c->stream));  // the caller may free its image right after this call
     if ((rc = b2mip_generate_mipmaps(c->sky, B2_QUALITY_BOX))) return rc;  // legacypbr.d:869
     c->launches += c->sky->launches;
-    // every level once more as a CUDA array with the gather flag: the lighting kernel reads the 2 x 2 footprints of the
-    // trilinear sample with texture gather (exact texels; the filter weights stay in FP32 in the kernel)
-    const int nl = (int)c->sky->levels.size();
-    c->skyArr.assign(nl, nullptr); c->skyTex.assign(nl, 0);
-    for (int l = 0; l < nl; ++l) {
-        const DevLevel& L = c->sky->levels[l];
+    // every level once more in ONE CUDA array with the gather flag (an atlas, each level with a replicated one-texel
+    // border): the lighting kernel reads the 2 x 2 footprints of the trilinear sample with texture gather (exact texels;
+    // the filter weights stay in FP32 in the kernel) through a single, warp-uniform texture handle
+    {
+        const int nl = (int)c->sky->levels.size();
+        int aw = 0, ah = 0;
+        sky_atlas_layout(c->sky->levels.data(), nl, c->skyOx, c->skyOy, &aw, &ah);
+        uint32_t* lin = nullptr;
+        CU(cudaMalloc((void**)&lin, (size_t)aw * ah * 4));
+        launch_sky_atlas(c->sky->levels.data(), nl, c->skyOx, c->skyOy, aw, ah, lin, c->stream);
+        c->launches++;
+        CU(cudaGetLastError());
         const cudaChannelFormatDesc fd = cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindUnsigned);
-        CU(cudaMallocArray(&c->skyArr[l], &fd, (size_t)L.w, (size_t)L.h, cudaArrayTextureGather));
-        CU(cudaMemcpy2DToArrayAsync(c->skyArr[l], 0, 0, L.base, (size_t)L.pitch, (size_t)L.w * 4, (size_t)L.h, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMallocArray(&c->skyArr, &fd, (size_t)aw, (size_t)ah, cudaArrayTextureGather));
+        CU(cudaMemcpy2DToArrayAsync(c->skyArr, 0, 0, lin, (size_t)aw * 4, (size_t)aw * 4, (size_t)ah, cudaMemcpyDeviceToDevice, c->stream));
         cudaResourceDesc rd;
         memset(&rd, 0, sizeof(rd));
         rd.resType = cudaResourceTypeArray;
-        rd.res.array.array = c->skyArr[l];
+        rd.res.array.array = c->skyArr;
         cudaTextureDesc td;
         memset(&td, 0, sizeof(td));
         td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
         td.filterMode = cudaFilterModePoint;
         td.readMode = cudaReadModeNormalizedFloat;
         td.normalizedCoords = 0;
-        CU(cudaCreateTextureObject(&c->skyTex[l], &rd, &td, nullptr));
+        CU(cudaCreateTextureObject(&c->skyTex, &rd, &td, nullptr));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(lin);
     }
     CU(cudaStreamSynchronize(c->stream));
     return B2_OK;

@@ -69,8 +69,11 @@ struct PbrArgs {
     // coordinates, normalised-float reads); the skybox levels are CUDA arrays read with texture gather
     cudaTextureObject_t texD[kMaxDiffuseLevels];   // diffuse levels (1..3 are sampled)
     cudaTextureObject_t texZ[kMaxDepthLevels];     // depth levels (1..4 are sampled)
-    cudaTextureObject_t texSky[kMaxSkyLevels];
+    // all skybox levels in ONE CUDA array (an atlas: every level with a one-texel replicated border around it), so that
+    // the texture handle of the gathers is warp-uniform while the level varies per pixel
+    cudaTextureObject_t texSky;
     float skyMaxX[kMaxSkyLevels], skyMaxY[kMaxSkyLevels];   // w - 1, h - 1 of every skybox level
+    float skyOx[kMaxSkyLevels], skyOy[kMaxSkyLevels];       // atlas position of texel (0, 0) of every level
 };
 
 }  // namespace b2

@@ -12,9 +12,10 @@
 //     The rolling-row machinery of pbr_fast.cu (staged windows of levels 1..3, refresh blocks, 26 registers of state)
 //     disappears; the fetches for row j+1 are issued while row j is shaded.
 //   * the trilinear skybox sample (linearMipmapSample, mipmap.d:149-160) fetches its 2 x 4 texels with texture GATHER
-//     (tld4, one instruction per channel and level) from per-level CUDA arrays: exact texel values, filter weights
-//     computed in FP32 exactly as before — only the address arithmetic, the eight dependent loads and the byte
-//     unpacking move to the texture unit.
+//     (tld4, one instruction per channel and level) from a CUDA array holding every skybox level (an atlas, each level
+//     with a replicated one-texel border: one warp-uniform texture handle although the level varies per pixel): exact
+//     texel values, filter weights computed in FP32 exactly as before — only the address arithmetic, the eight
+//     dependent loads and the byte unpacking move to the texture unit.
 //   * the bicubic levels 4 and 5 (16 / 32 pixels per texel) keep their four horizontally interpolated rows in registers.
 //
 // Work item = one CTA = a box of at most 64 x 64 pixels of one GUI tile (the host cuts areas into boxes of 64 x 2R
@@ -29,6 +30,7 @@
 //
 // Precondition (checked by the host): full pyramids, i.e. diffuse has levels 0..5 and depth 0..4 (every canvas of at
 // least 32x32 pixels).  Smaller canvases take the exact kernel.
+#include <cstring>
 #include "pbr_math.cuh"
 
 namespace b2 {
@@ -274,16 +276,18 @@ __global__ void __launch_bounds__(T_WARPS * 32, B2_TEX_MIN_CTAS) k_pbr_tex(const
     // ---------------------------------------------------------------- fetches of the first row
     uint32_t diffuseNext = __ldg(rowPtr<uint32_t>(P.diffuse[0], box.miny) + ic);
     uint32_t materialNext = __ldg(rowPtr<uint32_t>(P.material, box.miny) + ic);
-    float zNext = 0.f;          // sum of the four bilinear depth samples (normalised: / 65535)
-    G3 eNext{0, 0, 0};          // sum of the three bilinear diffuse samples (normalised: / 255)
+    // Raw results of the seven bilinear fetches of the NEXT row: they are summed only where the next row consumes them, a
+    // whole row of arithmetic later (summing at the fetch would wait for the texture unit right there)
+    float zA = 0.f, zB = 0.f, zC = 0.f, zD = 0.f;
+    float4 eA = {0, 0, 0, 0}, eB = eA, eC = eA;
     auto fetchMips = [&](const RowT& rr) {
-        if (needMipsZ)
-            zNext = (tex2D<float>(P.texZ[1], tu1, rr.tvZ[0]) + tex2D<float>(P.texZ[2], tu2, rr.tvZ[1])) +
-                    (tex2D<float>(P.texZ[3], tu3, rr.tvZ[2]) + tex2D<float>(P.texZ[4], tu4, rr.tvZ[3]));
+        if (needMipsZ) {
+            zA = tex2D<float>(P.texZ[1], tu1, rr.tvZ[0]); zB = tex2D<float>(P.texZ[2], tu2, rr.tvZ[1]);
+            zC = tex2D<float>(P.texZ[3], tu3, rr.tvZ[2]); zD = tex2D<float>(P.texZ[4], tu4, rr.tvZ[3]);
+        }
         if (needMipsD) {
-            const float4 a = tex2D<float4>(P.texD[1], tu1, rr.tvD[0]), b = tex2D<float4>(P.texD[2], tu2, rr.tvD[1]),
-                         c = tex2D<float4>(P.texD[3], tu3, rr.tvD[2]);
-            eNext = G3{(a.x + b.x) + c.x, (a.y + b.y) + c.y, (a.z + b.z) + c.z};
+            eA = tex2D<float4>(P.texD[1], tu1, rr.tvD[0]); eB = tex2D<float4>(P.texD[2], tu2, rr.tvD[1]);
+            eC = tex2D<float4>(P.texD[3], tu3, rr.tvD[2]);
         }
     };
     fetchMips(SW.rows[0]);
@@ -293,8 +297,8 @@ __global__ void __launch_bounds__(T_WARPS * 32, B2_TEX_MIN_CTAS) k_pbr_tex(const
 #pragma unroll
         for (int k = 0; k < 3; ++k) dp[k] = __fmul_rn(trow[T_COLS - 1 + k], multUshort);
         const uint32_t diffusePx = diffuseNext, materialPx = materialNext;
-        const float zMips = zNext;
-        const G3 eMips = eNext;
+        const float zMips = (zA + zB) + (zC + zD);   // normalised (/ 65535) sum of the four bilinear depth samples
+        const G3 eMips{(eA.x + eB.x) + eC.x, (eA.y + eB.y) + eC.y, (eA.z + eB.z) + eC.z};   // (/ 255) sum of the three diffuse samples
         const RowT& rs = SW.rows[j - box.miny];   // broadcast shared loads
         {   // prefetch the next row's pixels and mip samples (clamped on the last row: harmless re-read)
             const int jn = min(j + 1, yLast);
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(T_WARPS * 32, B2_TEX_MIN_CTAS) k_pbr_tex(const
         // shadow / directional / specular arithmetic, which then runs in their shadow; the blend follows after the
         // specular pass, where the reference adds the sky term (same order of additions into T)
         const bool doSky = HAS_SKY && (mask & 0x20u);
-        float4 gr = {0, 0, 0, 0}, gg = gr, gb = gr, hr = gr, hg = gr, hb = gr;
+        float4 gr, gg, gb, hr, hg, hb;
         float sfx = 0, sfy = 0, s2fx = 0, s2fy = 0, fl = 0;
         if (doSky) {
             float lod = variance * P.skyPixels;
@@ -381,19 +385,19 @@ __global__ void __launch_bounds__(T_WARPS * 32, B2_TEX_MIN_CTAS) k_pbr_tex(const
                 float x = fmaxf(fmaf(skyx, sc, -0.5f), 0.f), y = fmaxf(fmaf(skyy, sc, -0.5f), 0.f);
                 const float fxi = truncf(x), fyi = truncf(y);
                 fx = x - fxi; fy = y - fyi;
-                gx = fminf(fxi, P.skyMaxX[level]) + 1.0f;
-                gy = fminf(fyi, P.skyMaxY[level]) + 1.0f;
+                gx = (fminf(fxi, P.skyMaxX[level]) + 1.0f) + P.skyOx[level];   // small integers: exact
+                gy = (fminf(fyi, P.skyMaxY[level]) + 1.0f) + P.skyOy[level];
             };
             const int level = max(0, min(il, P.nSky - 1));
             float gx, gy;
             setup(level, sfx, sfy, gx, gy);
-            const cudaTextureObject_t t0 = P.texSky[level];
+            const cudaTextureObject_t t0 = P.texSky;
             gr = tex2Dgather<float4>(t0, gx, gy, 0); gg = tex2Dgather<float4>(t0, gx, gy, 1); gb = tex2Dgather<float4>(t0, gx, gy, 2);
-            if (fl != 0.f) {  // second level of the trilinear blend
+            {   // second level of the trilinear blend: fetched also when fl == 0 (integer level), where the reference returns
+                // the first level alone — the blend below then yields exactly that (sky + 0 * (sky1 - sky))
                 const int level2 = max(0, min(il + 1, P.nSky - 1));
                 setup(level2, s2fx, s2fy, gx, gy);
-                const cudaTextureObject_t t1 = P.texSky[level2];
-                hr = tex2Dgather<float4>(t1, gx, gy, 0); hg = tex2Dgather<float4>(t1, gx, gy, 1); hb = tex2Dgather<float4>(t1, gx, gy, 2);
+                hr = tex2Dgather<float4>(t0, gx, gy, 0); hg = tex2Dgather<float4>(t0, gx, gy, 1); hb = tex2Dgather<float4>(t0, gx, gy, 2);
             }
         }
 
@@ -455,28 +459,10 @@ __global__ void __launch_bounds__(T_WARPS * 32, B2_TEX_MIN_CTAS) k_pbr_tex(const
             T.z = fmaf(P.light3Col[2], k, T.z);
         }
 
-        // ---- PassSkyboxReflections, second half: blend the gathered texels (normalised floats, b / 255).
-        // gather component order: x = (i0, j1), y = (i1, j1), z = (i1, j0), w = (i0, j0)
-        if (doSky) {
-            auto bil = [](const float4& g, float fx, float fy) {
-                const float up = fmaf(fx, g.z - g.w, g.w), down = fmaf(fx, g.y - g.x, g.x);
-                return fmaf(fy, down - up, up);
-            };
-            G3 sky{bil(gr, sfx, sfy), bil(gg, sfx, sfy), bil(gb, sfx, sfy)};
-            if (fl != 0.f) {
-                const G3 sky1{bil(hr, s2fx, s2fy), bil(hg, s2fx, s2fy), bil(hb, s2fx, s2fy)};
-                sky = fma3(fl, sky1 - sky, sky);
-            }
-            float k = metal * P.skyAmount;
-            T.x = fmaf(sky.x, k, T.x);
-            T.y = fmaf(sky.y, k, T.y);
-            T.z = fmaf(sky.z, k, T.z);
-        }
-
-        G3 accum{base.x * T.x, base.y * T.y, base.z * T.z};
-
         // ---- PassEmissiveContribution (legacypbr.d:948-1007, non-legacy branch): diffuse levels 1..3 bilinear (texture
-        // units), 4 and 5 bicubic
+        // units), 4 and 5 bicubic.  Evaluated here, ahead of the sky blend, so that it runs in the shadow of the gathers too;
+        // it is added to the accumulator last, as in the reference.
+        G3 emitted{0, 0, 0};
         if (needMipsD) {
             if (refresh & 0x3) refreshCub(4, P.diffuse[4], SW.d4, 0, rs.ib4, (refresh & 0x1) != 0, p4);
             if (refresh & 0xc) refreshCub(5, P.diffuse[5], SW.d5, 2, rs.ib5, (refresh & 0x4) != 0, p5);
@@ -488,10 +474,28 @@ __global__ void __launch_bounds__(T_WARPS * 32, B2_TEX_MIN_CTAS) k_pbr_tex(const
             float noise = (tU16(__ldg(noisePtr + (j & 15))) - 127.5f) * 0.003f;
             const float AMT = 0.002f * 0.67f;
             float k5 = AMT * (1.0f + noise);
-            accum.x = fmaf(c5.x, k5, fmaf(c4.x, AMT, fmaf(eMips.x, AMT * 255.0f, accum.x)));
-            accum.y = fmaf(c5.y, k5, fmaf(c4.y, AMT, fmaf(eMips.y, AMT * 255.0f, accum.y)));
-            accum.z = fmaf(c5.z, k5, fmaf(c4.z, AMT, fmaf(eMips.z, AMT * 255.0f, accum.z)));
+            emitted.x = fmaf(c5.x, k5, fmaf(c4.x, AMT, eMips.x * (AMT * 255.0f)));
+            emitted.y = fmaf(c5.y, k5, fmaf(c4.y, AMT, eMips.y * (AMT * 255.0f)));
+            emitted.z = fmaf(c5.z, k5, fmaf(c4.z, AMT, eMips.z * (AMT * 255.0f)));
         }
+
+        // ---- PassSkyboxReflections, second half: blend the gathered texels (normalised floats, b / 255).
+        // gather component order: x = (i0, j1), y = (i1, j1), z = (i1, j0), w = (i0, j0)
+        if (doSky) {
+            auto bil = [](const float4& g, float fx, float fy) {
+                const float up = fmaf(fx, g.z - g.w, g.w), down = fmaf(fx, g.y - g.x, g.x);
+                return fmaf(fy, down - up, up);
+            };
+            G3 sky{bil(gr, sfx, sfy), bil(gg, sfx, sfy), bil(gb, sfx, sfy)};
+            const G3 sky1{bil(hr, s2fx, s2fy), bil(hg, s2fx, s2fy), bil(hb, s2fx, s2fy)};
+            sky = fma3(fl, sky1 - sky, sky);
+            float k = metal * P.skyAmount;
+            T.x = fmaf(sky.x, k, T.x);
+            T.y = fmaf(sky.y, k, T.y);
+            T.z = fmaf(sky.z, k, T.z);
+        }
+
+        const G3 accum{fmaf(base.x, T.x, emitted.x), fmaf(base.y, T.y, emitted.y), fmaf(base.z, T.z, emitted.z)};
 
         // ---- PassClampAndConvertTo8bit (legacypbr.d:1057-1107, non-legacy branch)
         if ((mask & 0x80u) && active) {
@@ -507,6 +511,48 @@ __global__ void __launch_bounds__(T_WARPS * 32, B2_TEX_MIN_CTAS) k_pbr_tex(const
 #pragma unroll
         for (int k = 0; k < 3; ++k) { dm[k] = d0[k]; d0[k] = dp[k]; }
     }
+}
+
+// Skybox atlas (set-up time): texel (x, y) of the atlas is the clamped texel of the level whose bordered rectangle
+// contains it, 0 elsewhere.  `ox / oy` = atlas position of texel (0, 0) of each level.
+struct SkyAtlasArgs {
+    DevLevel lv[kMaxSkyLevels];
+    int ox[kMaxSkyLevels], oy[kMaxSkyLevels];
+    int n, aw, ah;
+    uint32_t* out;   // gapless aw x ah
+};
+__global__ void __launch_bounds__(256) k_sky_atlas(const __grid_constant__ SkyAtlasArgs A) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= A.aw || y >= A.ah) return;
+    uint32_t v = 0;
+    for (int l = 0; l < A.n; ++l) {
+        const int lx = x - A.ox[l], ly = y - A.oy[l];
+        if (lx >= -1 && lx <= A.lv[l].w && ly >= -1 && ly <= A.lv[l].h) {
+            v = rowPtr<uint32_t>(A.lv[l], max(0, min(ly, A.lv[l].h - 1)))[max(0, min(lx, A.lv[l].w - 1))];
+            break;
+        }
+    }
+    A.out[(size_t)y * A.aw + x] = v;
+}
+// lays the levels out (level 0 at (1, 1), the others stacked in a column to its right) and fills `out` (aw * ah texels)
+void sky_atlas_layout(const DevLevel* levels, int n, int* ox, int* oy, int* aw, int* ah) {
+    ox[0] = 1; oy[0] = 1;
+    int y = 1, colW = 0;
+    const int x1 = levels[0].w + 3;
+    for (int l = 1; l < n; ++l) {
+        ox[l] = x1; oy[l] = y;
+        y += levels[l].h + 2;
+        if (levels[l].w > colW) colW = levels[l].w;
+    }
+    *aw = n > 1 ? x1 + colW + 1 : levels[0].w + 2;
+    *ah = (levels[0].h + 2 > y + 1 ? levels[0].h + 2 : y + 1);
+}
+void launch_sky_atlas(const DevLevel* levels, int n, const int* ox, const int* oy, int aw, int ah, uint32_t* out, cudaStream_t s) {
+    SkyAtlasArgs A;
+    memset(&A, 0, sizeof(A));
+    for (int l = 0; l < n; ++l) { A.lv[l] = levels[l]; A.ox[l] = ox[l]; A.oy[l] = oy[l]; }
+    A.n = n; A.aw = aw; A.ah = ah; A.out = out;
+    k_sky_atlas<<<dim3((aw + 31) / 32, (ah + 7) / 8), 256, 0, s>>>(A);
 }
 
 int pbr_tex_box_rows() { return T_BOX; }
