@@ -22,7 +22,7 @@ UNITS = [
     ("mip_fused.cu", ["-fmad=false"] + (["-DB2_MIP_DEBUG"] if os.environ.get("B2_MIP_DEBUG") else [])),
     ("pbr_exact.cu", ["-fmad=false"]),
     ("pbr_fast.cu", ["-DB2_MIN_CTAS=%s" % os.environ.get("B2_MIN_CTAS", "4")]),
-    ("pbr_tex.cu", ["-DB2_TEX_MIN_CTAS=%s" % os.environ.get("B2_TEX_MIN_CTAS", "4")]),
+    ("pbr_tex.cu", ["-DB2_TEX_MIN_CTAS=%s" % os.environ.get("B2_TEX_MIN_CTAS", "5")]),
 ]
 
 

@@ -34,7 +34,7 @@ void launch_fill32(const DevLevel& win, uint32_t value, cudaStream_t s);
 void launch_pbr_exact(const PbrArgs& args, int gridBlocks, cudaStream_t stream);
 void launch_pbr_fast(const PbrArgs& args, cudaStream_t stream);
 int pbr_fast_strip_rows();
-void launch_pbr_tex(const PbrArgs& args, cudaStream_t stream);
+void launch_pbr_tex(const PbrArgs& args, bool skyGather, cudaStream_t stream);
 void sky_atlas_layout(const DevLevel* levels, int n, int* ox, int* oy, int* aw, int* ah);
 void launch_sky_atlas(const DevLevel* levels, int n, const int* ox, const int* oy, int aw, int ah, uint32_t* out, cudaStream_t s);
 void launch_sample(const DevLevel* levels, int nLevels, int color, int kind, int n, const float* lvl, const float* x,
@@ -641,7 +641,7 @@ struct b2pbr {
     int needD[kMaxDiffuseLevels][2], needZ[kMaxDepthLevels][2];
     b2mip *diffuse = nullptr, *material = nullptr, *depth = nullptr, *sky = nullptr;
     cudaArray_t skyArr = nullptr;                 // every skybox level once more in one CUDA array (texture gather needs one)
-    cudaTextureObject_t skyTex = 0;
+    cudaTextureObject_t skyTex = 0, skyTexLin = 0;
     int skyOx[kMaxSkyLevels], skyOy[kMaxSkyLevels];   // atlas position of texel (0, 0) of each level
     DevLevel out{}; uint8_t* outAlloc = nullptr;
     DevLevel swz{}; uint8_t* swzAlloc = nullptr;
@@ -689,6 +689,8 @@ static void pbrInvalidateGraphs(b2pbr* c) {
 
 static void pbrFreeSkyTextures(b2pbr* c) {
     if (c->skyTex) cudaDestroyTextureObject(c->skyTex);
+    if (c->skyTexLin) cudaDestroyTextureObject(c->skyTexLin);
+    c->skyTexLin = 0;
     if (c->skyArr) cudaFreeArray(c->skyArr);
     c->skyTex = 0; c->skyArr = nullptr;
 }
@@ -928,7 +930,7 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
     // the throughput kernel assumes full pyramids (diffuse levels 0..5, depth 0..4: any canvas >= 32x32);
     // smaller canvases are shaded by the exact kernel
     const bool fast = c->mode != B2_MODE_EXACT && (int)diffuse->levels.size() >= kMaxDiffuseLevels && (int)depth->levels.size() >= kMaxDepthLevels;
-    int rc = pbrUploadBoxes(c, areas, n, !fast ? 0 : (c->mode == B2_MODE_FAST ? 2 : 1));
+    int rc = pbrUploadBoxes(c, areas, n, !fast ? 0 : (c->mode != B2_MODE_FAST_ROLLING ? 2 : 1));
     if (rc) return rc;
     if (usedFast) *usedFast = fast;
     if (c->nDeviceBoxes == 0) return B2_OK;
@@ -961,7 +963,7 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
         A.skyPixels = (float)(c->sky->W * c->sky->H);
         A.skyFX = (float)c->sky->W - 1.0f;
         A.skyFY = (float)c->sky->H - 1.0f;
-        A.texSky = c->skyTex;
+        A.texSky = c->skyTex; A.texSkyLin = c->skyTexLin;
         for (int l = 0; l < A.nSky; ++l) {
             A.skyMaxX[l] = (float)(c->sky->levels[l].w - 1);
             A.skyMaxY[l] = (float)(c->sky->levels[l].h - 1);
@@ -972,7 +974,7 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
     for (int l = 0; l < A.nDiffuse; ++l) A.texD[l] = diffuse->tex[l];
     for (int l = 0; l < A.nDepth; ++l) A.texZ[l] = depth->tex[l];
     traceBegin(c, "PBR compositeTile");
-    if (fast && c->mode == B2_MODE_FAST) launch_pbr_tex(A, c->stream);
+    if (fast && c->mode != B2_MODE_FAST_ROLLING) launch_pbr_tex(A, c->mode == B2_MODE_FAST_SKY_GATHER, c->stream);
     else if (fast) launch_pbr_fast(A, c->stream);
     else launch_pbr_exact(A, A.nBoxes, c->stream);
     c->launches++;
@@ -1117,7 +1119,7 @@ int b2pbr_set_params(b2pbr* c, const b2pbr_params* p) {
     return B2_OK;
 }
 int b2pbr_set_mode(b2pbr* c, int mode) {
-    if (!c || (mode != B2_MODE_FAST && mode != B2_MODE_EXACT && mode != B2_MODE_FAST_ROLLING)) return fail(B2_ERR_INVALID, "set_mode: bad arguments");
+    if (!c || (mode != B2_MODE_FAST && mode != B2_MODE_EXACT && mode != B2_MODE_FAST_ROLLING && mode != B2_MODE_FAST_SKY_GATHER)) return fail(B2_ERR_INVALID, "set_mode: bad arguments");
     if (mode != c->mode) pbrInvalidateGraphs(c);
     c->mode = mode;
     return B2_OK;
@@ -1173,6 +1175,8 @@ int b2pbr_set_skybox(b2pbr* c, const uint8_t* rgba, int w, int h, size_t pitch) 
         td.readMode = cudaReadModeNormalizedFloat;
         td.normalizedCoords = 0;
         CU(cudaCreateTextureObject(&c->skyTex, &rd, &td, nullptr));
+        td.filterMode = cudaFilterModeLinear;
+        CU(cudaCreateTextureObject(&c->skyTexLin, &rd, &td, nullptr));
         CU(cudaStreamSynchronize(c->stream));
         cudaFree(lin);
     }
@@ -1475,7 +1479,7 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
     const int R0 = stripRowsFor(areas, n_areas);
     auto workItems = [&](int k, const b2_box2i& a, bool fast) {   // k = index in the sorted list that is uploaded
         if (!fast) return 1;
-        const bool boxes = c->mode == B2_MODE_FAST;               // k_pbr_tex: CTA boxes of 64 x 2R; k_pbr_fast: strips of 32 x R
+        const bool boxes = c->mode != B2_MODE_FAST_ROLLING;       // k_pbr_tex: CTA boxes of 64 x 2R; k_pbr_fast: strips of 32 x R
         const int R = stripRowsOfAreaAt(c, k, n_areas, a, R0) * (boxes ? 2 : 1), bw = boxes ? 64 : 32;
         return ((boxH(a) + R - 1) / R) * ((boxW(a) + bw - 1) / bw);
     };

@@ -72,6 +72,7 @@ struct PbrArgs {
     // all skybox levels in ONE CUDA array (an atlas: every level with a one-texel replicated border around it), so that
     // the texture handle of the gathers is warp-uniform while the level varies per pixel
     cudaTextureObject_t texSky;
+    cudaTextureObject_t texSkyLin;   // the same array with the linear filter (B2_SKY_HW experiment)
     float skyMaxX[kMaxSkyLevels], skyMaxY[kMaxSkyLevels];   // w - 1, h - 1 of every skybox level
     float skyOx[kMaxSkyLevels], skyOy[kMaxSkyLevels];       // atlas position of texel (0, 0) of every level
 };

@@ -123,8 +123,10 @@ __device__ __forceinline__ void tCubCoord(int l, int p, int& ib, float& t) {
     t = (float)(n1 & ((2 << l) - 1)) * levelScale(l + 1);
 }
 
-template <bool HAS_SKY, bool ALL_PASSES>
-__global__ void __launch_bounds__(T_WARPS * 32, B2_TEX_MIN_CTAS) k_pbr_tex(const __grid_constant__ PbrArgs P) {
+// SKY_GATHER: the skybox footprints are fetched with texture gather and blended with FP32 weights (exact reference
+// weights); otherwise the two bilinear samples use the texture unit's filter (8-bit weights; see the header comment)
+template <bool HAS_SKY, bool ALL_PASSES, bool SKY_GATHER>
+__global__ void __launch_bounds__(T_WARPS * 32, SKY_GATHER ? 4 : B2_TEX_MIN_CTAS) k_pbr_tex(const __grid_constant__ PbrArgs P) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     CtaT& S = *reinterpret_cast<CtaT*>(smemRaw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -378,6 +380,18 @@ __global__ void __launch_bounds__(T_WARPS * 32, B2_TEX_MIN_CTAS) k_pbr_tex(const
             float skyy = fmaf(fmaf(ry, 0.5f, 0.5f), P.skyFY, 0.5f);
             int il = __float2int_rz(lod);               // linearMipmapSample, mipmap.d:149-160
             fl = lod - (float)il;
+            if (!SKY_GATHER) {
+            // the two bilinear samples on the texture unit's filter.  The atlas position of the sample is clamped to the
+            // level's texel centres, which reproduces the reference's edge rules (x < 0 -> 0; index clamp at w - 1)
+            auto hw = [&](int level) {
+                const float sc = levelScale(level);
+                const float cx = fminf(fmaxf(fmaf(skyx, sc, P.skyOx[level]), P.skyOx[level] + 0.5f), P.skyOx[level] + P.skyMaxX[level] + 0.5f);
+                const float cy = fminf(fmaxf(fmaf(skyy, sc, P.skyOy[level]), P.skyOy[level] + 0.5f), P.skyOy[level] + P.skyMaxY[level] + 0.5f);
+                return tex2D<float4>(P.texSkyLin, cx, cy);
+            };
+            gr = hw(max(0, min(il, P.nSky - 1)));
+            hr = hw(max(0, min(il + 1, P.nSky - 1)));
+            } else {
             // coordinate set-up of Mipmap.linearSample (mipmap.d:309-342) with the texel fetch left to the gather: the
             // footprint of a gather at (ix + 1, iy + 1) is exactly texels ix, min(ix + 1, w - 1) x iy, min(iy + 1, h - 1)
             auto setup = [&](int level, float& fx, float& fy, float& gx, float& gy) {
@@ -398,6 +412,7 @@ __global__ void __launch_bounds__(T_WARPS * 32, B2_TEX_MIN_CTAS) k_pbr_tex(const
                 const int level2 = max(0, min(il + 1, P.nSky - 1));
                 setup(level2, s2fx, s2fy, gx, gy);
                 hr = tex2Dgather<float4>(t0, gx, gy, 0); hg = tex2Dgather<float4>(t0, gx, gy, 1); hb = tex2Dgather<float4>(t0, gx, gy, 2);
+            }
             }
         }
 
@@ -482,13 +497,17 @@ __global__ void __launch_bounds__(T_WARPS * 32, B2_TEX_MIN_CTAS) k_pbr_tex(const
         // ---- PassSkyboxReflections, second half: blend the gathered texels (normalised floats, b / 255).
         // gather component order: x = (i0, j1), y = (i1, j1), z = (i1, j0), w = (i0, j0)
         if (doSky) {
-            auto bil = [](const float4& g, float fx, float fy) {
-                const float up = fmaf(fx, g.z - g.w, g.w), down = fmaf(fx, g.y - g.x, g.x);
-                return fmaf(fy, down - up, up);
-            };
-            G3 sky{bil(gr, sfx, sfy), bil(gg, sfx, sfy), bil(gb, sfx, sfy)};
-            const G3 sky1{bil(hr, s2fx, s2fy), bil(hg, s2fx, s2fy), bil(hb, s2fx, s2fy)};
-            sky = fma3(fl, sky1 - sky, sky);
+            G3 sky;
+            if (!SKY_GATHER) sky = G3{fmaf(fl, hr.x - gr.x, gr.x), fmaf(fl, hr.y - gr.y, gr.y), fmaf(fl, hr.z - gr.z, gr.z)};
+            else {
+                auto bil = [](const float4& g, float fx, float fy) {
+                    const float up = fmaf(fx, g.z - g.w, g.w), down = fmaf(fx, g.y - g.x, g.x);
+                    return fmaf(fy, down - up, up);
+                };
+                sky = G3{bil(gr, sfx, sfy), bil(gg, sfx, sfy), bil(gb, sfx, sfy)};
+                const G3 sky1{bil(hr, s2fx, s2fy), bil(hg, s2fx, s2fy), bil(hb, s2fx, s2fy)};
+                sky = fma3(fl, sky1 - sky, sky);
+            }
             float k = metal * P.skyAmount;
             T.x = fmaf(sky.x, k, T.x);
             T.y = fmaf(sky.y, k, T.y);
@@ -558,27 +577,32 @@ void launch_sky_atlas(const DevLevel* levels, int n, const int* ox, const int* o
 int pbr_tex_box_rows() { return T_BOX; }
 
 static bool g_texAttrSet[64];
-void launch_pbr_tex(const PbrArgs& args, cudaStream_t stream) {
+template <bool SKY, bool ALL, bool GATHER>
+static void launchTexT(const PbrArgs& args, size_t smem, bool setAttr, cudaStream_t stream) {
+    if (setAttr) cudaFuncSetAttribute(k_pbr_tex<SKY, ALL, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else k_pbr_tex<SKY, ALL, GATHER><<<args.nBoxes, T_WARPS * 32, smem, stream>>>(args);
+}
+static void dispatchTex(const PbrArgs& args, bool gather, size_t smem, bool setAttr, cudaStream_t stream) {
+    const bool all = setAttr ? true : (args.passMask & 0xffu) == 0xffu, sky = setAttr ? true : args.nSky > 0;
+    for (int pass = 0; pass < (setAttr ? 6 : 1); ++pass) {     // setAttr: every instantiation once
+        const bool s = setAttr ? (pass < 4) : sky, a = setAttr ? (pass & 1) : all, g = setAttr ? (pass & 2) != 0 : (gather && sky);
+        if (s && a && g) launchTexT<true, true, true>(args, smem, setAttr, stream);
+        else if (s && a) launchTexT<true, true, false>(args, smem, setAttr, stream);
+        else if (s && g) launchTexT<true, false, true>(args, smem, setAttr, stream);
+        else if (s) launchTexT<true, false, false>(args, smem, setAttr, stream);
+        else if (a) launchTexT<false, true, false>(args, smem, setAttr, stream);
+        else launchTexT<false, false, false>(args, smem, setAttr, stream);
+    }
+}
+void launch_pbr_tex(const PbrArgs& args, bool skyGather, cudaStream_t stream) {
     const size_t smem = sizeof(CtaT);
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !g_texAttrSet[dev]) {  // > 48 KB of dynamic shared memory is an opt-in, per device
-        cudaFuncSetAttribute(k_pbr_tex<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pbr_tex<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pbr_tex<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pbr_tex<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dispatchTex(args, false, smem, true, stream);
         g_texAttrSet[dev] = true;
     }
-    const bool all = (args.passMask & 0xffu) == 0xffu;
-    const dim3 block(T_WARPS * 32);
-    const int grid = args.nBoxes;
-    if (args.nSky > 0) {
-        if (all) k_pbr_tex<true, true><<<grid, block, smem, stream>>>(args);
-        else k_pbr_tex<true, false><<<grid, block, smem, stream>>>(args);
-    } else {
-        if (all) k_pbr_tex<false, true><<<grid, block, smem, stream>>>(args);
-        else k_pbr_tex<false, false><<<grid, block, smem, stream>>>(args);
-    }
+    dispatchTex(args, skyGather, smem, false, stream);
 }
 
 }  // namespace b2

@@ -44,11 +44,18 @@ enum {
 };
 /* the maps GUIGraphics owns and lends to the compositor — gui/dplug/gui/graphics.d:117-122 */
 enum { B2_MAP_DIFFUSE = 0, B2_MAP_MATERIAL = 1, B2_MAP_DEPTH = 2 };
-/* lighting kernels: FAST = throughput kernel (texture units for the mip samplers, FMA / MUFU; +-1 LSB contract);
- * EXACT = the reference's IEEE operation order, bit-identical to the CPU restatement (several times slower; the
- * device-side yardstick); FAST_ROLLING = round 1's throughput kernel (samplers in FP32 from shared-memory windows;
- * kept for A/B measurements, same contract) */
-enum { B2_MODE_FAST = 0, B2_MODE_EXACT = 1, B2_MODE_FAST_ROLLING = 2 };
+/* lighting kernels (all but EXACT under the +-1 LSB contract of BASELINE.json):
+ *   FAST            = throughput kernel: the bilinear mip samplers and the skybox samples run on the texture units
+ *                     (pixel-centre samples of the pyramids have weights the 8-bit hardware filter represents exactly;
+ *                     the skybox samples do not: their weight error is at most 2^-8 per axis, i.e. at most
+ *                     skyboxAmount * metalness * (|dAB| + |dCD|) / 256 LSB of a channel — measured 0.2 % of channels
+ *                     flipping by 1 LSB on the synthetic frames);
+ *   FAST_SKY_GATHER = the same kernel with the skybox footprints fetched by texture gather and blended with the
+ *                     reference's FP32 weights (15 % slower);
+ *   EXACT           = the reference's IEEE operation order, bit-identical to the CPU restatement (several times slower;
+ *                     the device-side yardstick);
+ *   FAST_ROLLING    = round 1's throughput kernel (samplers in FP32 from shared-memory windows; kept for A/B runs). */
+enum { B2_MODE_FAST = 0, B2_MODE_EXACT = 1, B2_MODE_FAST_ROLLING = 2, B2_MODE_FAST_SKY_GATHER = 3 };
 /* window pixel orders for the fused post-composite swizzle — window/dplug/window/window.d WindowPixelFormat */
 enum { B2_PF_RGBA8 = 0, B2_PF_BGRA8 = 1, B2_PF_ARGB8 = 2 };
 

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 TOL_LSB = 1
 
 
-MODES = [0, 1]  # B2_MODE_FAST (what ships by default), B2_MODE_EXACT
+MODES = [0, 1, 3]  # B2_MODE_FAST (what ships by default), B2_MODE_EXACT, B2_MODE_FAST_SKY_GATHER
 
 
 def _setup(b2, oracle, W, H, depth_kind="smooth", seed=synth.SEED, sky=True, params=None, threads=8, mode=0):
