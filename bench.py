@@ -42,7 +42,7 @@ def config_for(workload, n_gpus):
     """the `config` object — identical for the b200 arm and the reference arm (arm-specific detail lives elsewhere)"""
     W, H, desc = WORKLOADS[workload]
     return {"workload": desc, "width": W, "height": H, "tile": "64x64", "n_gpus": n_gpus,
-            "call_shape": "regenerateMipmaps(dirty = whole frame) + compositeTile(64x64 tile list), update_rects = NULL as the D shim passes",
+            "call_shape": "regenerateMipmaps(dirty = whole frame) + compositeTile(64x64 tile list) per frame (device-resident: as one b2pbr_redraw call; host images: update_rects = NULL as the D shim passes)",
             "l2": "inputs larger than the 126 MB L2 (independent frames visited round-robin / a canvas of several hundred MB per GPU)"}
 
 
@@ -128,7 +128,7 @@ def _traffic(key):
     with its provenance; `stale` = the kernel source changed since the capture."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))[key]
-        src = _sha1(os.path.join(ROOT, "dplug_b200", "csrc", "pbr_fast.cu"))
+        src = _sha1(os.path.join(ROOT, "dplug_b200", "csrc", "pbr_tex.cu"))
         return int(t["dram_bytes_read"] + t["dram_bytes_write"]), {"file": "profiles/dram_traffic.json", "capture": t.get("source"),
                                                                    "kernel_source_sha1_at_capture": t.get("kernel_source_sha1"),
                                                                    "kernel_source_sha1_now": src,
@@ -263,7 +263,7 @@ def _timed(stream, step, steps, barrier, min_seconds=0.0):
 
 
 def frame_bench(local, W, H, instances, steps, warmup, graph=True, batch=False, batch_streams=4, rank=0, world=1, dist=None,
-                e2e=True, sustained=True, mip_fusion=1):
+                e2e=True, sustained=True, mip_fusion=1, redraw=True):
     """device-resident + host-image timing of full-frame composites of WxH UIs on one GPU (C1 / C2 / C4 shapes)"""
     import numpy as np
     import torch
@@ -302,8 +302,13 @@ def frame_bench(local, W, H, instances, steps, warmup, graph=True, batch=False, 
         if graph and (i % R) in graphs:
             c.graphLaunch(graphs[i % R])     # the same two calls, replayed from a CUDA graph
             return
-        c.regenerateMipmaps(whole)       # GUIGraphics.regenerateMipmaps, whole frame dirty
-        c.compositeTile(None, tiles)     # GUIGraphics.compositeGUI -> ICompositor.compositeTile
+        # GUIGraphics.doDraw stages C + D: regenerateMipmaps (whole frame dirty) then compositeGUI -> compositeTile, as the
+        # one call (b2pbr_redraw; --redraw 0: the two separate calls — same device work)
+        if redraw:
+            c.redraw(whole, tiles)
+        else:
+            c.regenerateMipmaps(whole)
+            c.compositeTile(None, tiles)
 
     def step(i):
         if batch:
@@ -328,7 +333,11 @@ def frame_bench(local, W, H, instances, steps, warmup, graph=True, batch=False, 
     barrier()
     if graph:
         for k, c in enumerate(comps):
-            c.graphBegin(); c.regenerateMipmaps(whole); c.compositeTile(None, tiles)
+            c.graphBegin()
+            if redraw:
+                c.redraw(whole, tiles)
+            else:
+                c.regenerateMipmaps(whole); c.compositeTile(None, tiles)
             graphs[k] = c.graphEnd()
         for i in range(1 if batch else R):
             step(i)
@@ -641,7 +650,7 @@ def run_default_single(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     _set_affinity(local)
-    r = frame_bench(local, W, H, args.instances, args.steps, args.warmup, graph=bool(args.graph), mip_fusion=args.mip_fusion)
+    r = frame_bench(local, W, H, args.instances, args.steps, args.warmup, graph=bool(args.graph), mip_fusion=args.mip_fusion, redraw=bool(args.redraw))
     peak, peak_src = _peak()
     B = algorithmic_bytes_frame(W, H)
     achieved = B / (r["light_ms"] * 1e-3) / 1e9
@@ -655,7 +664,7 @@ def run_default_single(args):
                     "l2": "%d independent frames (%.0f MB) visited round-robin" % (r["R"], r["R"] * B / 1e6)},
         "sustained": dict(r.get("sustained", {}), value=W * H / (r["sustained"]["ms_per_step"] * 1e-3) / 1e6) if "sustained" in r else None,
         "frame_roofline_frac": (B / (r["ms_per_step"] * 1e-3) / 1e9) / peak,
-        "roofline": {"bound": "hbm", "kernel": "k_pbr_fast (fused lighting, 8 passes)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_pbr_tex (fused lighting, 8 passes; mip and skybox samplers on the texture units)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": B, "launch_ms": r["light_ms"],
                      "note": "the lighting pass is FP32-issue-bound (the reference's arithmetic is ~700 instructions per pixel against 16 B): "
@@ -764,7 +773,7 @@ def run_workload(args):
                    "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                    "scaling": "strong" if batch else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_for(wl, world),
                    "details": {"instances_per_gpu": r["R"], "cuda_graph": bool(args.graph)}, "sustained": r.get("sustained"),
-                   "roofline": {"bound": "hbm", "kernel": "k_pbr_fast (fused lighting, 8 passes)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                   "roofline": {"bound": "hbm", "kernel": "k_pbr_tex (fused lighting, 8 passes; mip and skybox samplers on the texture units)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": B, "launch_ms": r["light_ms"]},
                    "e2e": r.get("e2e"), "gpu_launches": r["launches"], "clocks": r.get("clocks")}
             if world == 1 and not args.no_cpu_baseline and wl in ("c1", "c2"):
@@ -795,6 +804,7 @@ def main():
     ap.add_argument("--c3-data", default="both", choices=["both", "random", "survey"])
     ap.add_argument("--mip-fusion", type=int, default=1, choices=[0, 1, 2],
                     help="0: one launch per generateLevel call; 1 (default): small levels fused; 2: every level fused")
+    ap.add_argument("--redraw", type=int, default=1, help="1: one b2pbr_redraw call per frame; 0: regenerateMipmaps + compositeTile (the same device work)")
     ap.add_argument("--graph", type=int, default=1, help="replay each frame's device work from a CUDA graph (1) or launch kernel by kernel (0)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -84,6 +84,7 @@ SIGNATURES = {
     "b2pbr_regenerate_mipmaps": (C.c_int, [C.c_void_p, C.POINTER(box2i), C.c_int]),
     "b2pbr_regenerate_mipmaps_on": (C.c_int, [C.c_void_p, C.POINTER(box2i), C.c_int, C.c_void_p]),
     "b2pbr_composite_tile": (C.c_int, [C.c_void_p, C.POINTER(box2i), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2pbr_redraw": (C.c_int, [C.c_void_p, C.POINTER(box2i), C.c_int, C.POINTER(box2i), C.c_int]),
     "b2pbr_composite_tile_host": (C.c_int, [C.c_void_p, imageref, C.POINTER(box2i), C.c_int, C.POINTER(box2i), C.c_int,
                                             imageref, imageref, imageref]),
     "b2pbr_composite_tile_host_begin": (C.c_int, [C.c_void_p, imageref, C.POINTER(box2i), C.c_int, C.POINTER(box2i), C.c_int,

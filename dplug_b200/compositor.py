@@ -210,6 +210,11 @@ class PBRCompositor:
         else:
             _lib.check(self._l.b2pbr_regenerate_mipmaps_on(self._h, _lib.boxes(rects), len(rects), C.c_void_p(stream)))
 
+    def redraw(self, updateRects, areas):
+        """regenerateMipmaps(updateRects) + compositeTile(areas) as one call (GUIGraphics.doDraw runs them back to back,
+        graphics.d:812-821)."""
+        _lib.check(self._l.b2pbr_redraw(self._h, _lib.boxes(updateRects), len(updateRects), _lib.boxes(areas), len(areas)))
+
     def compositeGUI(self, rectsToCompositeDisjointed, wfb=None):
         """GUIGraphics.compositeGUI — gui/dplug/gui/graphics.d:1338-1349."""
         tiles = tileAreas(rectsToCompositeDisjointed, PBR_TILE_MAX_WIDTH, PBR_TILE_MAX_HEIGHT)

@@ -198,6 +198,11 @@ int b2pbr_regenerate_mipmaps_on(b2pbr*, const b2_box2i* rects, int n, void* cuda
  * Passing NULL maps uses the compositor's own twins. */
 int b2pbr_composite_tile(b2pbr*, const b2_box2i* areas, int n, b2mip* diffuse, b2mip* material, b2mip* depth);
 
+/* One frame on device-resident maps = GUIGraphics.regenerateMipmaps() followed by compositeGUI() (what doDraw does back
+ * to back, gui/dplug/gui/graphics.d:812-821): b2pbr_regenerate_mipmaps(update_rects) + b2pbr_composite_tile(areas) as ONE
+ * call.  Same pyramid levels and the same frame as the two calls. */
+int b2pbr_redraw(b2pbr*, const b2_box2i* update_rects, int n_update, const b2_box2i* areas, int n_areas);
+
 /* Same call with HOST images, exactly the reference's arguments: uploads `areas` (grown by the sampling
  * reach where needed: see DESIGN.md) of the three level-0 maps, regenerates the device mip levels the
  * passes sample, composites, and copies `areas` of the result into wfb.  update_rects/n_update are

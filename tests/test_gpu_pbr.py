@@ -451,3 +451,41 @@ def test_graph_invalidation_and_raw_bounds(b2):
     for bad in [(0, 0, W + 1, 10), (-1, 0, 10, 10), (0, H - 4, 8, H + 4)]:
         with pytest.raises(b2.B2Error):
             c.compositeRaw([bad])
+
+
+@pytest.mark.parametrize("W,H", [(3840, 2160), (1000, 1300), (700, 520), (2048, 1024)])
+def test_redraw_equals_two_calls(b2, W, H):
+    """b2pbr_redraw (regenerateMipmaps + compositeTile as one call, GUIGraphics.doDraw stages C + D): the same frame and the
+    same pyramid levels, byte for byte, as the two separate calls — also from a stale pyramid, replayed from a CUDA graph,
+    and after the content changed."""
+    d, m, z = synth.frame(W, H)
+    sky = synth.skybox(128, 96)
+    tiles = b2.BoxArray(b2.tileAreas([(0, 0, W, H)], 64, 64)); whole = b2.BoxArray([(0, 0, W, H)])
+    a = b2.PBRCompositor(0); a.resizeBuffers(W, H); a.setSkybox(sky)
+    b = b2.PBRCompositor(0); b.resizeBuffers(W, H); b.setSkybox(sky)
+    rng = np.random.default_rng(3)
+    for c in (a, b):
+        c.diffuseMap.upload(0, d); c.materialMap.upload(0, m); c.depthMap.upload(0, z)
+    for l in range(1, 6):      # stale levels: the redraw must regenerate every texel of every level
+        lw, lh = W >> l, H >> l
+        b.diffuseMap.upload(l, rng.integers(0, 256, size=(lh, lw, 4), dtype=np.uint8))
+        if l < 5:
+            b.depthMap.upload(l, rng.integers(0, 65536, size=(lh, lw), dtype=np.uint16))
+    a.regenerateMipmaps(whole); a.compositeTile(None, tiles)
+    want = a.download()
+    b.redraw(whole, tiles)
+    assert np.array_equal(b.download(), want)
+    for l in range(1, 6):
+        assert np.array_equal(a.diffuseMap.download(l), b.diffuseMap.download(l)), l
+    for l in range(1, 5):
+        assert np.array_equal(a.depthMap.download(l), b.depthMap.download(l)), l
+    # recorded into a graph, replayed on new content
+    b.graphBegin(); b.redraw(whole, tiles); g = b.graphEnd()
+    d2, m2, z2 = synth.frame(W, H, synth.SEED + 11)
+    for c in (a, b):
+        c.diffuseMap.upload(0, d2); c.materialMap.upload(0, m2); c.depthMap.upload(0, z2)
+    a.regenerateMipmaps(whole); a.compositeTile(None, tiles)
+    b.graphLaunch(g)
+    assert np.array_equal(b.download(), a.download())
+    for l in range(1, 6):
+        assert np.array_equal(a.diffuseMap.download(l), b.diffuseMap.download(l)), l
