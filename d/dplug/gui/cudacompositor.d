@@ -50,6 +50,24 @@ extern(C) nothrow @nogc
                                   b2_imageref diffuseL0, b2_imageref materialL0, b2_imageref depthL0);
     int b2_host_register(void* ptr, size_t bytes);
     int b2_host_unregister(void* ptr);
+    int b2pbr_profile_enable(b2pbr*, int on);
+    int b2pbr_trace_json(b2pbr*, char* buf, size_t cap, size_t* needed);
+
+    // ---- multi-GPU row bands (one canvas cut into horizontal bands, one band object per GPU)
+    struct b2band;
+    int b2pbr_create_band(b2pbr** o, int device, int y0, int y1);
+    b2mip* b2pbr_map(b2pbr*, int which);   // 0 diffuse, 1 material, 2 depth
+    int b2mip_upload(b2mip*, int level, const(void)* host, size_t hostPitch, const(b2_box2i)* rects, int n);
+    int b2pbr_download(b2pbr*, void* host, size_t hostPitch, const(b2_box2i)* rects, int n);
+    int b2_band_rows(int H, int nranks, int rank, int align_, int* y0, int* y1);
+    int b2_band_nccl_unique_id(void* id128);
+    int b2band_create_nccl(b2band** o, b2pbr* band, int rank, int nranks, const(int)* bandY, const(void)* id128, void* ncclComm);
+    int b2band_create_peers(b2band** o, const(b2pbr*)* bands, int nranks);
+    void b2band_destroy(b2band*);
+    int b2band_exchange_begin(b2band*);
+    int b2band_exchange_end(b2band*);
+    int b2band_composite_frame(b2band*);
+    int b2band_sync(b2band*);
 }
 
 /// ICompositor backed by the B200 library.  Same calls, same arguments, same threading contract as
@@ -95,10 +113,27 @@ nothrow:
         }
         b2_imageref out_ = b2_imageref(wfb.w, wfb.h, wfb.pitch, cast(void*) wfb.pixels);
         static assert(box2i.sizeof == b2_box2i.sizeof);
+        // the host's profiler sees the call as one span, like a pass of the reference (profiler.d:29-64); the per-stage
+        // device times are available as Chrome Trace JSON (b2pbr_profile_enable + traceJSON below, same format as
+        // TraceProfiler, profiler.d:177-207)
+        version(Dplug_ProfileUI) if (profiler !is null) profiler.category("gpu").begin("b2pbr compositeTile");
+        // update_rects = null: the tile list IS what changed (the library coalesces it: a full-frame list becomes one
+        // rectangle and takes the fused mip chain and the pipelined transfer)
         int rc = b2pbr_composite_tile_host(_h, out_, cast(const(b2_box2i)*) areas.ptr, cast(int) areas.length,
                                            null, 0,
                                            toC(diffuseMap.levels[0]), toC(materialMap.levels[0]), toC(depthMap.levels[0]));
+        version(Dplug_ProfileUI) if (profiler !is null) profiler.end();
         assert(rc == 0);
+    }
+
+    /// Device-side stage times of the calls since enableDeviceTrace(true), as Chrome Trace Event JSON (what TraceProfiler
+    /// writes, profiler.d:177-207); `buf` receives at most buf.length bytes, the return value is the size needed.
+    void enableDeviceTrace(bool on) { b2pbr_profile_enable(_h, on ? 1 : 0); }
+    size_t deviceTraceJSON(char[] buf)
+    {
+        size_t needed;
+        b2pbr_trace_json(_h, buf.ptr, buf.length, &needed);
+        return needed;
     }
 
     // <LEGACY> setters, legacypbr.d:75-123
@@ -133,4 +168,66 @@ private:
     b2pbr* _h;
     b2pbr_params _params;
     void push() { int rc = b2pbr_set_params(_h, &_params); assert(rc == 0); }
+}
+
+/// One large canvas composited by several GPUs of one box: horizontal bands of whole 64-row tiles, one band object per
+/// GPU, all driven from this process (PEERS transport: halo rows are pushed GPU to GPU by the copy engines).  For one
+/// process per GPU use b2band_create_nccl instead (see INTEGRATION.md section 4).  The caller owns the host images of
+/// the WHOLE canvas, exactly as GUIGraphics does; every frame the bands upload their own rows, exchange the halo rows,
+/// composite, and the rows come back into `wfb`.
+final class CudaBandedCompositor
+{
+nothrow:
+@nogc:
+    this(int width, int height, int numDevices)
+    {
+        _w = width; _h = height; _n = numDevices;
+        _bands = mallocSlice!(b2pbr*)(numDevices);
+        _rows = mallocSlice!(int[2])(numDevices);
+        foreach (r; 0 .. numDevices)
+        {
+            int y0, y1;
+            b2_band_rows(height, numDevices, r, 64, &y0, &y1);
+            _rows[r] = [y0, y1];
+            int rc = b2pbr_create_band(&_bands[r], r, y0, y1);
+            assert(rc == 0);
+            rc = b2pbr_resize(_bands[r], width, height, 64, 64);
+            assert(rc == 0);
+        }
+        int rc = b2band_create_peers(&_group, cast(const(b2pbr*)*) _bands.ptr, numDevices);
+        assert(rc == 0, "bands thinner than the bloom reach (94 rows), or no peer access");
+    }
+
+    ~this()
+    {
+        if (_group) b2band_destroy(_group);
+        foreach (b; _bands) if (b) b2pbr_destroy(b);
+        freeSlice(_bands);
+        freeSlice(_rows);
+    }
+
+    /// GUIGraphics.regenerateMipmaps + compositeGUI for the whole canvas (full redraw)
+    void compositeFrame(ImageRef!RGBA wfb, OwnedImage!RGBA diffuse, OwnedImage!RGBA material, OwnedImage!L16 depth)
+    {
+        foreach (r; 0 .. _n)
+        {
+            b2_box2i own = b2_box2i(0, _rows[r][0], _w, _rows[r][1]);
+            b2mip_upload(b2pbr_map(_bands[r], 0), 0, diffuse.scanlinePtr(0), diffuse.pitchInBytes(), &own, 1);
+            b2mip_upload(b2pbr_map(_bands[r], 1), 0, material.scanlinePtr(0), material.pitchInBytes(), &own, 1);
+            b2mip_upload(b2pbr_map(_bands[r], 2), 0, depth.scanlinePtr(0), depth.pitchInBytes(), &own, 1);
+        }
+        int rc = b2band_composite_frame(_group);   // enqueues every band's frame, halo exchange included
+        assert(rc == 0);
+        foreach (r; 0 .. _n)
+        {
+            b2_box2i own = b2_box2i(0, _rows[r][0], _w, _rows[r][1]);
+            b2pbr_download(_bands[r], wfb.pixels, wfb.pitch, &own, 1);   // synchronises that band's stream
+        }
+    }
+
+private:
+    int _w, _h, _n;
+    b2pbr*[] _bands;
+    int[2][] _rows;
+    b2band* _group;
 }

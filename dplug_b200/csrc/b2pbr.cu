@@ -264,7 +264,7 @@ static int mipGenerateLevel(b2mip* m, int level, int quality, b2_box2i r) {
 // ---- fused chain (mip_fused.cu).  `rects[k]` is the update rectangle of level first + k, `q[k]` the quality of the
 // step producing it; exactly the result of n successive mipGenerateLevel calls.
 static bool g_mipFusion = true;
-static long long g_mipFuseBelow = 1ll << 20;   // source levels up to this many texels start a fused group
+static long long g_mipFuseBelow = getenv("B2_MIP_FUSE_BELOW") ? atoll(getenv("B2_MIP_FUSE_BELOW")) : (1ll << 20);   // source levels up to this many texels start a fused group (env: tuning aid)
 
 static int mipGenerateGroup(b2mip* m, int first, int n, const int* q, const b2_box2i* rects) {
     FusedArgs a{};
@@ -482,7 +482,7 @@ int b2mip_generate_chain(b2mip* m, int first_quality, int cubic_from_level) {
 int b2_set_mip_fusion(int enabled) {
     const int was = g_mipFusion ? (g_mipFuseBelow >= (1ll << 40) ? 2 : 1) : 0;
     g_mipFusion = enabled != 0;
-    g_mipFuseBelow = enabled == 2 ? (1ll << 40) : (1ll << 20);
+    g_mipFuseBelow = enabled == 2 ? (1ll << 40) : (getenv("B2_MIP_FUSE_BELOW") ? atoll(getenv("B2_MIP_FUSE_BELOW")) : (1ll << 20));
     return was;
 }
 int b2mip_sample(b2mip* m, int kind, int n, const float* level, const float* x, const float* y, float* out4) {
@@ -824,13 +824,18 @@ static int stripRowsFor(const b2_box2i* areas, int n) {
     static const int forced = getenv("B2_STRIP_ROWS") ? atoi(getenv("B2_STRIP_ROWS")) : 0;   // tuning aid
     if (forced >= 1 && forced <= pbr_fast_strip_rows()) return forced;
     const int full = pbr_fast_strip_rows();
-    int R = full;
-    for (; R > 4; R >>= 1) {
+    // Wave model: a launch runs ceil(strips / resident warps) waves, each as long as one strip (R rows + a staging cost
+    // worth ~6 rows).  Long lists take full-height strips (least staging per pixel); short ones — the 620 x 330 default
+    // UI, the boundary tiles of a row band — are cut finer when that fills the last wave better.
+    const long long slots = 148ll * 20;            // 5 CTAs x 4 warps per SM
+    int best = full; long long bestCost = -1;
+    for (int R = full; R >= 4; R >>= 1) {
         long long strips = 0;
         for (int k = 0; k < n; ++k) strips += (long long)((boxH(areas[k]) + R - 1) / R) * ((boxW(areas[k]) + 31) / 32);
-        if (strips >= 148 * 16) break;
+        const long long cost = ((strips + slots - 1) / slots) * (R + 6);
+        if (bestCost < 0 || cost < bestCost) { bestCost = cost; best = R; }
     }
-    return R;
+    return best;
 }
 
 // Strip height of area k of an n-area list.  Tail balancing: CTAs are dispatched in list order and a frame is only a

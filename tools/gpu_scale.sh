@@ -1,14 +1,12 @@
 #!/bin/bash
-# multi-GPU session on one 8-GPU box: C5 (16384^2 canvas, row bands, strong scaling) at N = 1, 2, 4, 8 and the default
-# workload (independent frames, weak scaling) at N = 8
-mkdir -p gpurun_out
-nvidia-smi -L | head -8
-python bench.py --workload c5 --steps 10 > gpurun_out/r1g_c5_n1.json 2> gpurun_out/r1g_c5_n1.err; tail -c 700 gpurun_out/r1g_c5_n1.json
-for N in 2 4 8; do
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500+N)) bench.py --gpus $N --workload c5 --steps 10 > gpurun_out/r1g_c5_n$N.json 2> gpurun_out/r1g_c5_n$N.err
-  tail -c 700 gpurun_out/r1g_c5_n$N.json; tail -3 gpurun_out/r1g_c5_n$N.err | cut -c1-300
-done
-for N in 2 8; do
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600+N)) bench.py --gpus $N --steps 100 --warmup 3 > gpurun_out/r1g_c2_n$N.json 2> gpurun_out/r1g_c2_n$N.err
-tail -c 900 gpurun_out/r1g_c2_n$N.json; tail -3 gpurun_out/r1g_c2_n$N.err | cut -c1-300
+# strong-scaling sweep of the default multi-GPU workload (C5 row bands) on one 8-GPU box: N = 8, 4, 2, then the N = 1 line
+T=${1:-r2}
+for N in 8 4 2; do
+  B2_BAND_DEBUG=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500+N)) bench.py --gpus $N --steps 50 --warmup 3 --extras 0 > gpurun_out/${T}_scale_n$N.json 2> gpurun_out/${T}_scale_n$N.err
+  grep b2band gpurun_out/${T}_scale_n$N.err | head -3
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/${T}_scale_n$N.json"))
+print($N, d["ms_per_step"], d["sustained"]["ms_per_step"], d["parity"]["bands_equal_unbanded_frame"], d["strong_scaling_in_this_run"], "e2e", d["e2e"]["ms_per_frame"])
+PY
 done
