@@ -142,7 +142,7 @@ static int mipAllocate(b2mip* m, int maxLevel) {
     CU(cudaMemsetAsync(m->alloc, 0, total, m->stream));
     for (int l = 0; l < n; ++l) m->levels[l].base = m->alloc + offs[l];
     m->tex.assign(n, 0);
-    for (int l = 0; l < n; ++l) {
+    for (int l = 1; l < n; ++l) {      // level 0 is never sampled through a texture (and may exceed the 65000-row limit of pitch-2D textures)
         const DevLevel& L = m->levels[l];
         if (L.w <= 0 || L.rows <= 0) continue;
         cudaResourceDesc rd;

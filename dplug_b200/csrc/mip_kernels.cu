@@ -3,6 +3,7 @@
 // two (box) or four (cubic) source rows and writes one vector of destination texels; warps cover
 // contiguous row segments.  Integer paths are bit-exact by construction; the alpha-premultiplying box
 // is float but uses only IEEE * and + (this file is compiled with -fmad=false).
+#include <cstdlib>
 #include "mip_math.cuh"
 
 namespace b2 {
@@ -218,6 +219,116 @@ __global__ void __launch_bounds__(256) k_cubic_rgba4(DevLevel dst, DevLevel src,
     }
 }
 
+// Walking variant for LARGE rectangles (generateLevelCubicRGBA, mipmap.d:902-1040; same integer arithmetic, same bytes).
+// The one-launch-of-loads-per-thread kernels above fetch every source row twice (the [1 3 3 1] footprints of
+// neighbouring destination rows overlap by two rows) and a thread's life is one round trip to memory.  Here a WARP owns a
+// strip of 128 destination columns (lane: 4 texels = two 128-bit loads per source row) and walks down WALK_ROWS
+// destination rows: every source row is loaded once, the loads of the next row pair are in flight while the current pair
+// is summed, and the vertical filter is carried as ONE partial sum per column: with A, B, C, D = rows 2y-1 .. 2y+2 split
+// into even / odd byte lanes, V(y) = (A + 3B) + 3C + D and the carry for y + 1 is C + 3D.
+template <int WALK_ROWS>
+__global__ void __launch_bounds__(128) k_cubic_rgba_walk(DevLevel dst, DevLevel src, Box r) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * 4 + warp;
+    const int x = ((r.minx >> 2) << 2) + strip * 128 + lane * 4;       // first destination texel of this lane
+    const int yb = r.miny + blockIdx.y * WALK_ROWS;
+    const int ye = min(yb + WALK_ROWS, r.maxy);
+    const int sw = src.w, sh = src.h;
+    if (((r.minx >> 2) << 2) + strip * 128 >= r.maxx) return;          // whole warp outside
+    const bool active = x < r.maxx && 2 * x < sw;                      // (x + 3 >= r.minx holds by construction)
+    const bool vec = active && (2 * x + 7 < sw);
+    const unsigned full = 0xffffffffu;
+    // neighbour columns 2x-1 / 2x+8 come from the adjacent lanes' sums; lanes on a warp or image edge load them
+    const bool leftOk = __shfl_up_sync(full, (int)vec, 1) && lane > 0;
+    const bool rightOk = __shfl_down_sync(full, (int)active, 1) && lane < 31 && 2 * x + 8 < sw;
+    const int cxl = max(2 * x - 1, 0), cxr = min(2 * x + 8, sw - 1);
+
+    struct Row { uint4 a, b; uint32_t l, rr; };
+    auto loadRow = [&](int sy) {
+        Row v;
+        v.a = v.b = make_uint4(0, 0, 0, 0); v.l = v.rr = 0;
+        if (!active) return v;
+        const uint32_t* p = rowPtr<uint32_t>(src, max(0, min(sy, sh - 1)));
+        if (vec) {
+            v.a = __ldg(reinterpret_cast<const uint4*>(p + 2 * x));
+            v.b = __ldg(reinterpret_cast<const uint4*>(p + 2 * x + 4));
+        } else {
+            uint32_t t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = __ldg(p + min(2 * x + k, sw - 1));
+            v.a = make_uint4(t[0], t[1], t[2], t[3]); v.b = make_uint4(t[4], t[5], t[6], t[7]);
+        }
+        if (!leftOk) v.l = __ldg(p + cxl);
+        if (!rightOk) v.rr = __ldg(p + cxr);
+        return v;
+    };
+    // columns 0..9 = source columns 2x-1 .. 2x+8; even / odd byte lanes
+    auto split = [](const Row& v, uint32_t (&e)[10], uint32_t (&o)[10]) {
+        const uint32_t t[10] = {v.l, v.a.x, v.a.y, v.a.z, v.a.w, v.b.x, v.b.y, v.b.z, v.b.w, v.rr};
+#pragma unroll
+        for (int k = 0; k < 10; ++k) { e[k] = evenBytes(t[k]); o[k] = oddBytes(t[k]); }
+    };
+
+    uint32_t pe[10], po[10];                        // carry: A + 3B per column
+    {
+        uint32_t ae[10], ao[10], be[10], bo[10];
+        split(loadRow(2 * yb - 1), ae, ao);
+        split(loadRow(2 * yb), be, bo);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) { pe[k] = ae[k] + 3u * be[k]; po[k] = ao[k] + 3u * bo[k]; }
+    }
+    // DEPTH row pairs in flight.  (Measured: 3 pairs need 163 registers and run the 4096^2 -> 2048^2 level in 25.7 us
+    // against 18.1 us with one pair at 80 registers — with ~14 walking warps per SM it is occupancy, not the depth of one
+    // warp's queue, that hides the latency.)
+    constexpr int DEPTH = 1;
+    Row c[DEPTH], d[DEPTH];
+#pragma unroll
+    for (int k = 0; k < DEPTH; ++k)
+        if (yb + k < ye) { c[k] = loadRow(2 * (yb + k) + 1); d[k] = loadRow(2 * (yb + k) + 2); }
+    for (int y0 = yb; y0 < ye; y0 += DEPTH) {
+#pragma unroll
+    for (int k = 0; k < DEPTH; ++k) {
+        const int y = y0 + k;
+        if (y >= ye) break;
+        const Row cc = c[k], dd = d[k];
+        if (y + DEPTH < ye) { c[k] = loadRow(2 * (y + DEPTH) + 1); d[k] = loadRow(2 * (y + DEPTH) + 2); }
+        uint32_t ce[10], co[10], de[10], dO[10], ve[10], vo[10];
+        split(cc, ce, co); split(dd, de, dO);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            ve[k] = pe[k] + 3u * ce[k] + de[k];     // <= 8 * 255 per 16-bit lane
+            vo[k] = po[k] + 3u * co[k] + dO[k];
+            pe[k] = ce[k] + 3u * de[k];
+            po[k] = co[k] + 3u * dO[k];
+        }
+        // outer columns from the neighbouring lanes where they hold them
+        const uint32_t lE = __shfl_up_sync(full, ve[8], 1), lO = __shfl_up_sync(full, vo[8], 1);
+        const uint32_t rE = __shfl_down_sync(full, ve[1], 1), rO = __shfl_down_sync(full, vo[1], 1);
+        if (leftOk) { ve[0] = lE; vo[0] = lO; }
+        if (rightOk) { ve[9] = rE; vo[9] = rO; }
+        if (!active) continue;
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            // destination x+t: columns 2(x+t)-1 .. 2(x+t)+2 = indices 2t .. 2t+3; the right-most tap is clamped to the
+            // last source column (mipmap.d:934-935)
+            uint32_t e3 = ve[2 * t + 3], o3 = vo[2 * t + 3];
+            if (2 * (x + t) + 2 > sw - 1) { e3 = ve[2 * t + 2]; o3 = vo[2 * t + 2]; }
+            const uint32_t sl = (ve[2 * t] + e3) + 3u * (ve[2 * t + 1] + ve[2 * t + 2]) + 0x00200020u;
+            const uint32_t sh2 = (vo[2 * t] + o3) + 3u * (vo[2 * t + 1] + vo[2 * t + 2]) + 0x00200020u;
+            o[t] = ((sl >> 6) & 0x00ff00ffu) | (((sh2 >> 6) & 0x00ff00ffu) << 8);
+        }
+        uint32_t* dp = rowPtrW<uint32_t>(dst, y);
+        if (x >= r.minx && x + 3 < r.maxx) *reinterpret_cast<uint4*>(dp + x) = make_uint4(o[0], o[1], o[2], o[3]);
+        else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (x + t >= r.minx && x + t < r.maxx) dp[x + t] = o[t];
+        }
+    }
+    }
+}
+
 // L16 variant: thread = 2 destination texels; vertical sums are 32-bit per column (<= 8*65535).
 __global__ void __launch_bounds__(256) k_cubic_l16(DevLevel dst, DevLevel src, Box r) {
     const int xp = (r.minx >> 1) + blockIdx.x * blockDim.x + threadIdx.x;
@@ -417,6 +528,16 @@ void launch_box_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_
     k_box_l16<<<gridFor(quads, r.maxy - r.miny, block), block, 0, s>>>(dst, src, r);
 }
 void launch_cubic_rgba(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s) {
+    static const int walkOn = getenv("B2_CUBIC_WALK") ? atoi(getenv("B2_CUBIC_WALK")) : 1;   // tuning aid (0: never)
+    {   // large rectangles: walking warps, when there are enough of them to fill the GPU (8 per SM; measured on the 8192^2
+        // pyramid: 4096^2 -> 2048^2 in 18.1 us against 21.2 us; 8-row walks on 2048^2 -> 1024^2 were slower, 9.2 vs 8.2 us)
+        const int x0 = (r.minx >> 2) << 2;
+        const int strips = (r.maxx - x0 + 127) / 128, rows = r.maxy - r.miny;
+        if (walkOn && (long long)strips * ((rows + 15) / 16) >= 148 * 8) {
+            k_cubic_rgba_walk<16><<<dim3((strips + 3) / 4, (rows + 15) / 16), 128, 0, s>>>(dst, src, r);
+            return;
+        }
+    }
     dim3 block(32, 8);
     if (r.maxx - r.minx >= 256) {   // wide rectangles: four texels per thread
         int quads = ((r.maxx + 3) >> 2) - (r.minx >> 2);
