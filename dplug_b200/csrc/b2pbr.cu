@@ -961,6 +961,12 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
     memcpy(A.light3Dir, p.light3_dir, 12); memcpy(A.light3Col, p.light3_color, 12);
     A.ambient = p.ambient_light; A.skyAmount = p.skybox_amount; A.toneThr = p.tonemap_threshold; A.toneRatio = p.tonemap_ratio;
     A.passMask = p.pass_active_mask;
+    {
+        const float d255 = 1.0f / 255.0f;
+        for (int k = 0; k < 3; ++k) { A.light1S[k] = p.light1_color[k] * d255; A.light2ColS[k] = p.light2_color[k] * d255; A.light3ColS[k] = p.light3_color[k] * d255 * d255; }
+        A.ambientS = p.ambient_light * d255;
+        A.skyAmountS = p.skybox_amount * d255 * d255;
+    }
     memcpy(A.shadowW, c->shadowW, sizeof(A.shadowW));
     A.shadowInvTotal = c->shadowInvTotal;
     A.invW = 1.0f / (float)c->W; A.invH = 1.0f / (float)c->H;

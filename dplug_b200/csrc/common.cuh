@@ -65,6 +65,10 @@ struct PbrArgs {
     float shadowInvTotal;
     float invW, invH;
     float skyPixels, skyFX, skyFY;
+    // k_pbr_tex keeps base colour and material in byte units; these copies carry the folded 1/255 factors:
+    // light1S = light1 / 255, light2ColS = light2Col / 255, light3ColS = light3Col / 255^2 (base colour and specular
+    // amount), ambientS = ambient / 255, skyAmountS = skyAmount / 255^2 (base colour and metalness)
+    float light1S[3], light2ColS[3], light3ColS[3], ambientS, skyAmountS;
     // texture-unit path (pbr_tex.cu): every pyramid level is also a pitch-2D texture (linear filter, clamp, unnormalised
     // coordinates, normalised-float reads); the skybox levels are CUDA arrays read with texture gather
     cudaTextureObject_t texD[kMaxDiffuseLevels];   // diffuse levels (1..3 are sampled)

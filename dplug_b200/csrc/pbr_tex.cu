@@ -310,10 +310,10 @@ __global__ void __launch_bounds__(T_WARPS * 32, SKY_GATHER ? 4 : B2_TEX_MIN_CTAS
         }
         const int refresh = rs.refresh;
 
-        const G3 base = tRgb(diffusePx) * div255;
-        const float rough = tByte(materialPx, 0) * div255;
-        const float metal = tByte(materialPx, 1) * div255;
-        const float specAmt = tByte(materialPx, 2) * div255;
+        // base colour and material stay in byte units (0..255): their 1/255 factors are folded into the light constants
+        // the host passes pre-scaled (PbrArgs::*S) and into the constants below
+        const G3 base = tRgb(diffusePx);
+        const float roughB = tByte(materialPx, 0), metalB = tByte(materialPx, 1), specB = tByte(materialPx, 2);
         const int roughByte = materialPx & 0xff;
 
         // ---- PassComputeNormal (legacypbr.d:279-381) + computePlaneFittingNormal (ransac.d:53-121).
@@ -347,8 +347,10 @@ __global__ void __launch_bounds__(T_WARPS * 32, SKY_GATHER ? 4 : B2_TEX_MIN_CTAS
             nx = vx * inv; ny = vy * inv; nzc = 0.382658847856f * inv;
             // variance (legacypbr.d:356-377): second differences of the 3x3 window.  The reference sums raw depths
             // (exact); here they are rebuilt from d (relative error ~1e-7, the variance feeds no RSQRTSS)
-            float ddx = (d[0] + d[3] + d[6]) - 2.0f * (d[1] + d[4] + d[7]) + (d[2] + d[5] + d[8]);
-            float ddy = (d[0] + d[1] + d[2]) - 2.0f * (d[3] + d[4] + d[5]) + (d[6] + d[7] + d[8]);
+            // per row: s = left + right, X = s - 2 centre (horizontal second difference), R = s + centre (row sum)
+            const float s0 = d[0] + d[2], s1 = d[3] + d[5], s2 = d[6] + d[8];
+            const float ddx = (fmaf(-2.0f, d[1], s0) + fmaf(-2.0f, d[4], s1)) + fmaf(-2.0f, d[7], s2);
+            const float ddy = fmaf(-2.0f, s1 + d[4], (s0 + d[1]) + (s2 + d[7]));
             const float kVar2 = (4655.0f / 256.0f) * (4655.0f / 256.0f);
             variance = fmaf(ddx, ddx, ddy * ddy) * kVar2;
         }
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(T_WARPS * 32, SKY_GATHER ? 4 : B2_TEX_MIN_CTAS
         if (needMipsZ) {
             float diff = fmaf(zMips, -0.25f * 65535.0f, zc);
             float cavity = tFmaSat(diff, 1.0f / 23040, 1.0f);
-            const float amb = cavity * P.ambient;
+            const float amb = cavity * P.ambientS;
             T = G3{amb, amb, amb};
         }
 
@@ -439,20 +441,20 @@ __global__ void __launch_bounds__(T_WARPS * 32, SKY_GATHER ? 4 : B2_TEX_MIN_CTAS
                 lightL = fmaf(c2, P.shadowW[s], lightL);
             }
             float k = fmaf(lightL, 0.7f, lightR) * P.shadowInvTotal;
-            T.x = fmaf(P.light1[0], k, T.x);
-            T.y = fmaf(P.light1[1], k, T.y);
-            T.z = fmaf(P.light1[2], k, T.z);
+            T.x = fmaf(P.light1S[0], k, T.x);
+            T.y = fmaf(P.light1S[1], k, T.y);
+            T.z = fmaf(P.light1S[2], k, T.z);
         }
 
         // ---- PassDirectionalLight (legacypbr.d:636-666)
         if (mask & 8u) {
             float dot = fmaf(nzc, P.light2Dir[2], fmaf(ny, P.light2Dir[1], nx * P.light2Dir[0]));
             float f = fmaf(0.5f, dot, 0.5f);
-            float a = fmaf(rough, -0.5f, 0.24f);
+            float a = fmaf(roughB, -0.5f * div255, 0.24f);
             f = (f - a) * tRcp(1.0f - a);  // linmap(f, a, 1, 0, 1), core/dplug/core/math.d:25-28
-            T.x = fmaf(P.light2Col[0], f, T.x);
-            T.y = fmaf(P.light2Col[1], f, T.y);
-            T.z = fmaf(P.light2Col[2], f, T.z);
+            T.x = fmaf(P.light2ColS[0], f, T.x);
+            T.y = fmaf(P.light2ColS[1], f, T.y);
+            T.z = fmaf(P.light2ColS[2], f, T.z);
         }
 
         // ---- PassSpecularLight (legacypbr.d:720-813)
@@ -467,11 +469,11 @@ __global__ void __launch_bounds__(T_WARPS * 32, SKY_GATHER ? 4 : B2_TEX_MIN_CTAS
             float eF = exponent * Ft;
             float tok = (1.0f + eF) * tRcp(1.0f + exponent);
             float p = tPow(sf, eF);
-            float roughFactor = 10.0f * (1.0f - rough) * fmaf(metal, -0.5f, 1.0f);
-            float k = p * roughFactor * tok * specAmt;
-            T.x = fmaf(P.light3Col[0], k, T.x);
-            T.y = fmaf(P.light3Col[1], k, T.y);
-            T.z = fmaf(P.light3Col[2], k, T.z);
+            float roughFactor = fmaf(roughB, -10.0f * div255, 10.0f) * fmaf(metalB, -0.5f * div255, 1.0f);
+            float k = p * roughFactor * tok * specB;            // specular amount in byte units: light3ColS carries its 1/255
+            T.x = fmaf(P.light3ColS[0], k, T.x);
+            T.y = fmaf(P.light3ColS[1], k, T.y);
+            T.z = fmaf(P.light3ColS[2], k, T.z);
         }
 
         // ---- PassEmissiveContribution (legacypbr.d:948-1007, non-legacy branch): diffuse levels 1..3 bilinear (texture
@@ -508,7 +510,7 @@ __global__ void __launch_bounds__(T_WARPS * 32, SKY_GATHER ? 4 : B2_TEX_MIN_CTAS
                 const G3 sky1{bil(hr, s2fx, s2fy), bil(hg, s2fx, s2fy), bil(hb, s2fx, s2fy)};
                 sky = fma3(fl, sky1 - sky, sky);
             }
-            float k = metal * P.skyAmount;
+            float k = metalB * P.skyAmountS;
             T.x = fmaf(sky.x, k, T.x);
             T.y = fmaf(sky.y, k, T.y);
             T.z = fmaf(sky.z, k, T.z);

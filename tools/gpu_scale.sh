@@ -10,3 +10,6 @@ d=json.load(open("gpurun_out/${T}_scale_n$N.json"))
 print($N, d["ms_per_step"], d["sustained"]["ms_per_step"], d["parity"]["bands_equal_unbanded_frame"], d["strong_scaling_in_this_run"], "e2e", d["e2e"]["ms_per_frame"])
 PY
 done
+# host-memory / PCIe ceiling with 8 and 1 ranks copying at once (what bounds the e2e figures)
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 tools/probes/host_bw_probe.py 2>/dev/null | grep host_bw | tee gpurun_out/${T}_host_bw.txt
+python tools/probes/host_bw_probe.py 2>/dev/null | grep host_bw | tee -a gpurun_out/${T}_host_bw.txt
