@@ -654,7 +654,7 @@ def run_default_single(args):
     peak, peak_src = _peak()
     B = algorithmic_bytes_frame(W, H)
     achieved = B / (r["light_ms"] * 1e-3) / 1e9
-    traffic, tsrc = _traffic("k_pbr_fast@%dx%d" % (W, H))
+    traffic, tsrc = _traffic("k_pbr_tex@%dx%d" % (W, H))
     out = {
         "metric": METRIC, "value": W * H / (r["ms_per_step"] * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
@@ -725,7 +725,7 @@ def run_default_multi(args):
             "parity": r["parity"],
             "strong_scaling_in_this_run": {"one_gpu_ms_same_canvas": single, "speedup": (single / r["ms_per_step"]) if single else None, "n_gpus": world},
             "frame_roofline_frac": (B / (r["ms_per_step"] * 1e-3) / 1e9) / (peak * world), "peak_source": peak_src,
-            "roofline": {"bound": "hbm", "kernel": "whole banded frame (k_pbr_fast + mip chain + halo exchange)", "achieved": B / (r["ms_per_step"] * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "whole banded frame (k_pbr_tex + mip chain + halo exchange)", "achieved": B / (r["ms_per_step"] * 1e-3) / 1e9,
                          "peak": peak * world, "unit": "GB/s", "frac": (B / (r["ms_per_step"] * 1e-3) / 1e9) / (peak * world), "traffic": None,
                          "algorithmic_bytes_per_launch": B},
             "e2e": r.get("e2e"), "secondary": sec,

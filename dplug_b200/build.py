@@ -15,13 +15,12 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-ftz=false", "-prec-div=true", "-prec-sqrt=true"]
 
 # (source, extra flags).  The integer mip kernels and the exact lighting kernel must not contract a*b+c
-# into FMA (the reference's SSE code has none); pbr_fast.cu is free to.
+# into FMA (the reference's SSE code has none); pbr_tex.cu is free to.
 UNITS = [
     ("b2pbr.cu", ["-fmad=false"]),
     ("mip_kernels.cu", ["-fmad=false"]),
     ("mip_fused.cu", ["-fmad=false"] + (["-DB2_MIP_DEBUG"] if os.environ.get("B2_MIP_DEBUG") else [])),
     ("pbr_exact.cu", ["-fmad=false"]),
-    ("pbr_fast.cu", ["-DB2_MIN_CTAS=%s" % os.environ.get("B2_MIN_CTAS", "4")]),
     ("pbr_tex.cu", ["-DB2_TEX_MIN_CTAS=%s" % os.environ.get("B2_TEX_MIN_CTAS", "5")]),
 ]
 

@@ -17,7 +17,7 @@
 #include "host_rects.hpp"
 
 namespace b2 {
-// kernels (mip_kernels.cu, mip_fused.cu, pbr_exact.cu, pbr_fast.cu)
+// kernels (mip_kernels.cu, mip_fused.cu, pbr_exact.cu, pbr_tex.cu)
 void launch_box_rgba(const DevLevel& dst, const DevLevel& src, Box r, bool premul, cudaStream_t s);
 void launch_box_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
 void launch_cubic_rgba(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s);
@@ -32,8 +32,7 @@ void launch_layer(bool blend, const DevLevel* dst3, const DevLevel* src3, const 
 void launch_present(const DevLevel& win, const DevLevel& src, Box box, int dx, int dy, int pf, const uint8_t* lut, cudaStream_t s);
 void launch_fill32(const DevLevel& win, uint32_t value, cudaStream_t s);
 void launch_pbr_exact(const PbrArgs& args, int gridBlocks, cudaStream_t stream);
-void launch_pbr_fast(const PbrArgs& args, cudaStream_t stream);
-int pbr_fast_strip_rows();
+constexpr int kQuadrantRows = 32;   // rows of a full-height warp quadrant of k_pbr_tex (CTA box = 64 x 64)
 void launch_pbr_tex(const PbrArgs& args, bool skyGather, cudaStream_t stream);
 void sky_atlas_layout(const DevLevel* levels, int n, int* ox, int* oy, int* aw, int* ah);
 void launch_sky_atlas(const DevLevel* levels, int n, const int* ox, const int* oy, int aw, int ah, uint32_t* out, cudaStream_t s);
@@ -823,8 +822,8 @@ struct b2pbr;
 static int stripRowsOfAreaAt(const b2pbr* c, int k, int n, const b2_box2i& a, int R0);
 static int stripRowsFor(const b2_box2i* areas, int n) {
     static const int forced = getenv("B2_STRIP_ROWS") ? atoi(getenv("B2_STRIP_ROWS")) : 0;   // tuning aid
-    if (forced >= 1 && forced <= pbr_fast_strip_rows()) return forced;
-    const int full = pbr_fast_strip_rows();
+    if (forced >= 1 && forced <= kQuadrantRows) return forced;
+    const int full = kQuadrantRows;
     // Wave model: a launch runs ceil(strips / resident warps) waves, each as long as one strip (R rows + a staging cost
     // worth ~6 rows).  Long lists take full-height strips (least staging per pixel); short ones — the 620 x 330 default
     // UI, the boundary tiles of a row band — are cut finer when that fills the last wave better.
@@ -846,12 +845,12 @@ static int stripRowsFor(const b2_box2i* areas, int n) {
 static int stripRowsOfAreaAt(const b2pbr* c, int k, int n, const b2_box2i& a, int R0) {
     static const int tailPct = getenv("B2_TAIL_PCT") ? atoi(getenv("B2_TAIL_PCT")) : 8;   // tuning aid
     int R = stripRowsOfArea(a, R0, c->tailRow, c->tailRow2);
-    if (R0 == pbr_fast_strip_rows() && k >= n - n * tailPct / 100 && R > 8) R = 8;
+    if (R0 == kQuadrantRows && k >= n - n * tailPct / 100 && R > 8) R = 8;
     return R;
 }
 
-// Uploads the work list of a launch.  kind 0: the caller's areas as they are (one CTA each); kind 1: the areas cut
-// into warp-sized strips of 32 columns x strip_rows rows for k_pbr_fast.  The list is kept on the device and
+// Uploads the work list of a launch.  kind 0: the caller's areas as they are (one CTA each, k_pbr_exact); kind 2: the
+// areas cut into CTA boxes of 64 columns x 2R rows for k_pbr_tex.  The list is kept on the device and
 // re-used while the caller passes the same areas (a full-frame tile list never changes between frames).
 static int pbrUploadBoxes(b2pbr* c, const b2_box2i* areas, int n, int kind) {
     for (auto& wl : c->workLists)
@@ -866,13 +865,12 @@ static int pbrUploadBoxes(b2pbr* c, const b2_box2i* areas, int n, int kind) {
     std::vector<Box> work;
     if (kind == 0) work.assign((const Box*)areas, (const Box*)areas + n);
     else {
-        // kind 1 (k_pbr_fast): warp strips of 32 columns x R rows; kind 2 (k_pbr_tex): CTA boxes of 64 columns x 2R rows,
-        // whose four warps take the four 32 x R quadrants
+        // CTA boxes of 64 columns x 2R rows, whose four warps take the four 32 x R quadrants
         const int R0 = stripRowsFor(areas, n);
-        const int bw = kind == 2 ? 64 : 32;
+        const int bw = 64;
         for (int k = 0; k < n; ++k) {
             const b2_box2i& a = areas[k];
-            const int R = stripRowsOfAreaAt(c, k, n, a, R0) * (kind == 2 ? 2 : 1);
+            const int R = stripRowsOfAreaAt(c, k, n, a, R0) * 2;
             for (int y = a.min_y; y < a.max_y; y += R)
                 for (int x = a.min_x; x < a.max_x; x += bw)
                     work.push_back(Box{x, y, x + bw < a.max_x ? x + bw : a.max_x, y + R < a.max_y ? y + R : a.max_y});
@@ -936,7 +934,7 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
     // the throughput kernel assumes full pyramids (diffuse levels 0..5, depth 0..4: any canvas >= 32x32);
     // smaller canvases are shaded by the exact kernel
     const bool fast = c->mode != B2_MODE_EXACT && (int)diffuse->levels.size() >= kMaxDiffuseLevels && (int)depth->levels.size() >= kMaxDepthLevels;
-    int rc = pbrUploadBoxes(c, areas, n, !fast ? 0 : (c->mode != B2_MODE_FAST_ROLLING ? 2 : 1));
+    int rc = pbrUploadBoxes(c, areas, n, fast ? 2 : 0);
     if (rc) return rc;
     if (usedFast) *usedFast = fast;
     if (c->nDeviceBoxes == 0) return B2_OK;
@@ -986,8 +984,7 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
     for (int l = 0; l < A.nDiffuse; ++l) A.texD[l] = diffuse->tex[l];
     for (int l = 0; l < A.nDepth; ++l) A.texZ[l] = depth->tex[l];
     traceBegin(c, "PBR compositeTile");
-    if (fast && c->mode != B2_MODE_FAST_ROLLING) launch_pbr_tex(A, c->mode == B2_MODE_FAST_SKY_GATHER, c->stream);
-    else if (fast) launch_pbr_fast(A, c->stream);
+    if (fast) launch_pbr_tex(A, c->mode == B2_MODE_FAST_SKY_GATHER, c->stream);
     else launch_pbr_exact(A, A.nBoxes, c->stream);
     c->launches++;
     traceEnd(c);
@@ -1133,7 +1130,7 @@ int b2pbr_set_params(b2pbr* c, const b2pbr_params* p) {
     return B2_OK;
 }
 int b2pbr_set_mode(b2pbr* c, int mode) {
-    if (!c || (mode != B2_MODE_FAST && mode != B2_MODE_EXACT && mode != B2_MODE_FAST_ROLLING && mode != B2_MODE_FAST_SKY_GATHER)) return fail(B2_ERR_INVALID, "set_mode: bad arguments");
+    if (!c || (mode != B2_MODE_FAST && mode != B2_MODE_EXACT && mode != B2_MODE_FAST_SKY_GATHER)) return fail(B2_ERR_INVALID, "set_mode: bad arguments");
     if (mode != c->mode) pbrInvalidateGraphs(c);
     c->mode = mode;
     return B2_OK;
@@ -1504,8 +1501,7 @@ static int pbrHostPipelined(b2pbr* c, b2_imageref wfb, const b2_box2i* areas, in
     const int R0 = stripRowsFor(areas, n_areas);
     auto workItems = [&](int k, const b2_box2i& a, bool fast) {   // k = index in the sorted list that is uploaded
         if (!fast) return 1;
-        const bool boxes = c->mode != B2_MODE_FAST_ROLLING;       // k_pbr_tex: CTA boxes of 64 x 2R; k_pbr_fast: strips of 32 x R
-        const int R = stripRowsOfAreaAt(c, k, n_areas, a, R0) * (boxes ? 2 : 1), bw = boxes ? 64 : 32;
+        const int R = stripRowsOfAreaAt(c, k, n_areas, a, R0) * 2, bw = 64;   // CTA boxes of 64 x 2R (k_pbr_tex)
         return ((boxH(a) + R - 1) / R) * ((boxW(a) + bw - 1) / bw);
     };
     // stage 1: every upload is enqueued up front, so the copy engine never waits for this thread (the host-side cost

@@ -2,7 +2,7 @@
 // gui/dplug/gui/legacypbr.d:269-1108 in registers with the reference's IEEE operation order (compiled
 // with -fmad=false), so its output equals the CPU restatement bit for bit.  The per-tile scratch images
 // of the reference (normal RGBf, variance L32f, accum RGBAf — legacypbr.d:41-55) never exist on the
-// device.  It is the device-side yardstick for the throughput kernel in pbr_fast.cu.
+// device.  It is the device-side yardstick for the throughput kernel in pbr_tex.cu.
 #include "pbr_math.cuh"
 
 namespace b2 {

@@ -1,6 +1,6 @@
 // Lighting kernel, throughput variant 2 (the one compositeTile launches by default): the texture-unit design.
 //
-// Same eight passes as gui/dplug/gui/legacypbr.d:269-1108, fused.  What changed against pbr_fast.cu (round 1, 790 warp
+// Same eight passes as gui/dplug/gui/legacypbr.d:269-1108, fused.  What changed against round 1's kernel (pbr_fast.cu in the history: 790 warp
 // instructions per pixel row, FP32-issue-bound) is WHO evaluates the mip samplers:
 //
 //   * the bilinear samplers — Mipmap!L16.linearSample of depth levels 1..4 (ambient occlusion, legacypbr.d:400-444) and
@@ -9,7 +9,7 @@
 //     coordinates).  The samplers are evaluated at pixel centres, (p + 0.5) * 2^-l, whose fractions are multiples of
 //     2^-(l+1) >= 1/32: exactly representable in the hardware's 8-bit filter weights, and clamp addressing reproduces the
 //     reference's edge rules (negative coordinate -> 0; upper index clamp after the fraction was taken, mipmap.d:309-339).
-//     The rolling-row machinery of pbr_fast.cu (staged windows of levels 1..3, refresh blocks, 26 registers of state)
+//     The rolling-row machinery of round 1 (staged windows of levels 1..3, refresh blocks, 26 registers of state)
 //     disappears; the fetches for row j+1 are issued while row j is shaded.
 //   * the trilinear skybox sample (linearMipmapSample, mipmap.d:149-160) fetches its 2 x 4 texels with texture GATHER
 //     (tld4, one instruction per channel and level) from a CUDA array holding every skybox level (an atlas, each level
@@ -100,7 +100,7 @@ __device__ __forceinline__ uint32_t tCvtU8(float f) {  // truncate, clamp to [0,
     asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(f));
     return r & 0xffu;
 }
-// RSQRTSS emulation for positive normal operands (see pbr_fast.cu / pbr_math.cuh rsqrtss_x86)
+// RSQRTSS emulation for positive normal operands (see pbr_math.cuh rsqrtss_x86)
 template <bool MAY_BE_ZERO = true>
 __device__ __forceinline__ float tRsqrtss(const uint32_t* __restrict__ tab, float x) {
     const uint32_t b = __float_as_uint(x);

@@ -53,9 +53,8 @@ enum { B2_MAP_DIFFUSE = 0, B2_MAP_MATERIAL = 1, B2_MAP_DEPTH = 2 };
  *   FAST_SKY_GATHER = the same kernel with the skybox footprints fetched by texture gather and blended with the
  *                     reference's FP32 weights (15 % slower);
  *   EXACT           = the reference's IEEE operation order, bit-identical to the CPU restatement (several times slower;
- *                     the device-side yardstick);
- *   FAST_ROLLING    = round 1's throughput kernel (samplers in FP32 from shared-memory windows; kept for A/B runs). */
-enum { B2_MODE_FAST = 0, B2_MODE_EXACT = 1, B2_MODE_FAST_ROLLING = 2, B2_MODE_FAST_SKY_GATHER = 3 };
+ *                     the device-side yardstick). */
+enum { B2_MODE_FAST = 0, B2_MODE_EXACT = 1, B2_MODE_FAST_SKY_GATHER = 3 };
 /* window pixel orders for the fused post-composite swizzle — window/dplug/window/window.d WindowPixelFormat */
 enum { B2_PF_RGBA8 = 0, B2_PF_BGRA8 = 1, B2_PF_ARGB8 = 2 };
 
