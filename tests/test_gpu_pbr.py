@@ -522,3 +522,41 @@ def test_dirty_rects_with_interacting_mip_chains(b2, oracle):
         for g in grown:
             _compare(got[g[1]:g[3], g[0]:g[2]], want[g[1]:g[3], g[0]:g[2]], "rects %s" % (g,))
         d2, m2, z2 = synth.frame(W, H, synth.SEED + 14, "smooth")
+
+
+def test_random_sizes_and_parameters(b2, oracle):
+    """Randomised sweep: odd canvas sizes, random light directions / colours / amounts, random pass masks, both depth
+    kinds and skybox sizes — throughput kernel (both skybox modes) within 1 LSB of the oracle, exact kernel identical."""
+    rng = np.random.default_rng(20261020)
+    for case in range(10):
+        W, H = int(rng.integers(33, 420)), int(rng.integers(33, 300))
+        kind = "noise" if case % 3 == 0 else "smooth"
+        p = b2.default_params()
+        for name in ("light1_color", "light2_color", "light3_color"):
+            setattr(p, name, (p.light1_color.__class__)(*[float(v) for v in rng.uniform(0.05, 0.6, 3)]))
+        for name in ("light2_dir", "light3_dir"):
+            v = rng.normal(size=3); v[2] = abs(v[2]) + 0.2; v = v / np.linalg.norm(v)
+            setattr(p, name, (p.light2_dir.__class__)(*[float(x) for x in v]))
+        p.ambient_light = float(rng.uniform(0.0, 0.3)); p.skybox_amount = float(rng.uniform(0.0, 0.9))
+        p.tonemap_threshold = float(rng.uniform(0.6, 1.2)); p.tonemap_ratio = float(rng.uniform(0.0, 0.6))
+        # (the normal pass stays on: the passes after it read its buffers, which the reference never clears)
+        p.pass_active_mask = 0xff if case % 2 == 0 else (int(rng.integers(0, 128)) | 0x81)
+        sky = case % 4 != 3
+        d, m, z = synth.frame(W, H, synth.SEED + 100 + case, kind)
+        s = synth.skybox(int(rng.integers(8, 300)), int(rng.integers(8, 200)), synth.SEED + case) if sky else None
+        ref = oracle.Graphics(W, H, numThreads=8)
+        if sky:
+            ref.setSkybox(s)
+        ref.set_params(p); ref.setInputs(d, m, z)
+        want = ref.fullFrame()
+        for mode in MODES:
+            c = b2.PBRCompositor(0); c.resizeBuffers(W, H); c.setMode(mode)
+            if sky:
+                c.setSkybox(s)
+            c.set_params(p)
+            c.diffuseMap.upload(0, d); c.materialMap.upload(0, m); c.depthMap.upload(0, z)
+            c.regenerateMipmaps([(0, 0, W, H)]); c.compositeGUI([(0, 0, W, H)])
+            got = c.download()
+            mx, frac = _compare(got, want, "case %d %dx%d mode %d mask %x" % (case, W, H, mode, p.pass_active_mask))
+            if mode == 1:
+                assert mx == 0, (case, mx, frac)
