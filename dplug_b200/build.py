@@ -18,7 +18,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-ftz=false",
 # into FMA (the reference's SSE code has none); pbr_tex.cu is free to.
 UNITS = [
     ("b2pbr.cu", ["-fmad=false"]),
-    ("mip_kernels.cu", ["-fmad=false"]),
+    ("mip_kernels.cu", ["-fmad=false"] + ["-D%s=%s" % (k, os.environ[k]) for k in ("B2_TMA_ROWS", "B2_TMA_STAGES") if k in os.environ]),
     ("mip_fused.cu", ["-fmad=false"] + (["-DB2_MIP_DEBUG"] if os.environ.get("B2_MIP_DEBUG") else [])),
     ("pbr_exact.cu", ["-fmad=false"]),
     ("pbr_tex.cu", ["-DB2_TEX_MIN_CTAS=%s" % os.environ.get("B2_TEX_MIN_CTAS", "5")]),

@@ -219,113 +219,145 @@ __global__ void __launch_bounds__(256) k_cubic_rgba4(DevLevel dst, DevLevel src,
     }
 }
 
-// Walking variant for LARGE rectangles (generateLevelCubicRGBA, mipmap.d:902-1040; same integer arithmetic, same bytes).
-// The one-launch-of-loads-per-thread kernels above fetch every source row twice (the [1 3 3 1] footprints of
-// neighbouring destination rows overlap by two rows) and a thread's life is one round trip to memory.  Here a WARP owns a
-// strip of 128 destination columns (lane: 4 texels = two 128-bit loads per source row) and walks down WALK_ROWS
-// destination rows: every source row is loaded once, the loads of the next row pair are in flight while the current pair
-// is summed, and the vertical filter is carried as ONE partial sum per column: with A, B, C, D = rows 2y-1 .. 2y+2 split
-// into even / odd byte lanes, V(y) = (A + 3B) + 3C + D and the carry for y + 1 is C + 3D.
-template <int WALK_ROWS>
-__global__ void __launch_bounds__(128) k_cubic_rgba_walk(DevLevel dst, DevLevel src, Box r) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int strip = blockIdx.x * 4 + warp;
-    const int x = ((r.minx >> 2) << 2) + strip * 128 + lane * 4;       // first destination texel of this lane
-    const int yb = r.miny + blockIdx.y * WALK_ROWS;
-    const int ye = min(yb + WALK_ROWS, r.maxy);
-    const int sw = src.w, sh = src.h;
-    if (((r.minx >> 2) << 2) + strip * 128 >= r.maxx) return;          // whole warp outside
-    const bool active = x < r.maxx && 2 * x < sw;                      // (x + 3 >= r.minx holds by construction)
-    const bool vec = active && (2 * x + 7 < sw);
-    const unsigned full = 0xffffffffu;
-    // neighbour columns 2x-1 / 2x+8 come from the adjacent lanes' sums; lanes on a warp or image edge load them
-    const bool leftOk = __shfl_up_sync(full, (int)vec, 1) && lane > 0;
-    const bool rightOk = __shfl_down_sync(full, (int)active, 1) && lane < 31 && 2 * x + 8 < sw;
-    const int cxl = max(2 * x - 1, 0), cxr = min(2 * x + 8, sw - 1);
+// TMA-fed variant for LARGE rectangles (generateLevelCubicRGBA, mipmap.d:902-1040; same integer arithmetic, same bytes).
+// A CTA owns a strip of TMA_STRIP destination columns and walks down TMA_ROWS destination rows.  One elected thread of a
+// producer warp streams the source rows of the strip into a shared-memory ring with 1-D bulk asynchronous copies
+// (cp.async.bulk.shared.global, the TMA engine: SASS UBLKCP) that complete on mbarriers; four consumer warps read a
+// stage when its barrier has flipped and hand it back through a second barrier.  No load instruction, no address
+// arithmetic and no scoreboard wait for global memory is left in the consumers' instruction stream, and TMA_STAGES row
+// pairs (33 KB) per CTA are in flight instead of what one round of register loads can hold.  The vertical [1 3 3 1] is
+// carried as one partial sum per column: with A..D = rows 2y-1 .. 2y+2 split into even / odd byte lanes,
+// V(y) = (A + 3B) + 3C + D and the carry for y + 1 is C + 3D, so every source row is read once.
+// Measured on the 8192^2 pyramid (4096^2 -> 2048^2, 84 MB): 18 us against 21.2 us for k_cubic_rgba4; a register-only
+// walking variant (loads by the consumers themselves, one row pair ahead) reached the same 18 us — at ~45 integer
+// instructions per destination texel (two 16-bit lanes per 32-bit operation) the level is bound by the ALU pipe, not by
+// HBM (13 us) — and a deeper register prefetch (163 registers) fell to 25.7 us.
+constexpr int TMA_STRIP = 256;                        // destination columns per CTA (128 consumer threads x 2 texels)
+#ifndef B2_TMA_ROWS
+#define B2_TMA_ROWS 16
+#endif
+#ifndef B2_TMA_STAGES
+#define B2_TMA_STAGES 4
+#endif
+constexpr int TMA_ROWS = B2_TMA_ROWS;                 // destination rows a CTA walks
+constexpr int TMA_STAGES = B2_TMA_STAGES;             // ring depth, in source-row pairs
+constexpr int TMA_ROW_TEXELS = 2 * TMA_STRIP + 8;     // source texels per staged row: columns [c0, c0 + 520), c0 = 2*x0 - 4
+constexpr int TMA_ROW_BYTES = TMA_ROW_TEXELS * 4;     // 2080, a multiple of 16
 
-    struct Row { uint4 a, b; uint32_t l, rr; };
-    auto loadRow = [&](int sy) {
-        Row v;
-        v.a = v.b = make_uint4(0, 0, 0, 0); v.l = v.rr = 0;
-        if (!active) return v;
-        const uint32_t* p = rowPtr<uint32_t>(src, max(0, min(sy, sh - 1)));
-        if (vec) {
-            v.a = __ldg(reinterpret_cast<const uint4*>(p + 2 * x));
-            v.b = __ldg(reinterpret_cast<const uint4*>(p + 2 * x + 4));
-        } else {
-            uint32_t t[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) t[k] = __ldg(p + min(2 * x + k, sw - 1));
-            v.a = make_uint4(t[0], t[1], t[2], t[3]); v.b = make_uint4(t[4], t[5], t[6], t[7]);
-        }
-        if (!leftOk) v.l = __ldg(p + cxl);
-        if (!rightOk) v.rr = __ldg(p + cxr);
-        return v;
-    };
-    // columns 0..9 = source columns 2x-1 .. 2x+8; even / odd byte lanes
-    auto split = [](const Row& v, uint32_t (&e)[10], uint32_t (&o)[10]) {
-        const uint32_t t[10] = {v.l, v.a.x, v.a.y, v.a.z, v.a.w, v.b.x, v.b.y, v.b.z, v.b.w, v.rr};
-#pragma unroll
-        for (int k = 0; k < 10; ++k) { e[k] = evenBytes(t[k]); o[k] = oddBytes(t[k]); }
-    };
-
-    uint32_t pe[10], po[10];                        // carry: A + 3B per column
-    {
-        uint32_t ae[10], ao[10], be[10], bo[10];
-        split(loadRow(2 * yb - 1), ae, ao);
-        split(loadRow(2 * yb), be, bo);
-#pragma unroll
-        for (int k = 0; k < 10; ++k) { pe[k] = ae[k] + 3u * be[k]; po[k] = ao[k] + 3u * bo[k]; }
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarArrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smemAddr(bar)), "r"(parity) : "memory");
+        if (spins > (1u << 26)) __trap();             // a lost completion aborts the launch instead of hanging the GPU
     }
-    // DEPTH row pairs in flight.  (Measured: 3 pairs need 163 registers and run the 4096^2 -> 2048^2 level in 25.7 us
-    // against 18.1 us with one pair at 80 registers — with ~14 walking warps per SM it is occupancy, not the depth of one
-    // warp's queue, that hides the latency.)
-    constexpr int DEPTH = 1;
-    Row c[DEPTH], d[DEPTH];
-#pragma unroll
-    for (int k = 0; k < DEPTH; ++k)
-        if (yb + k < ye) { c[k] = loadRow(2 * (yb + k) + 1); d[k] = loadRow(2 * (yb + k) + 2); }
-    for (int y0 = yb; y0 < ye; y0 += DEPTH) {
-#pragma unroll
-    for (int k = 0; k < DEPTH; ++k) {
-        const int y = y0 + k;
-        if (y >= ye) break;
-        const Row cc = c[k], dd = d[k];
-        if (y + DEPTH < ye) { c[k] = loadRow(2 * (y + DEPTH) + 1); d[k] = loadRow(2 * (y + DEPTH) + 2); }
-        uint32_t ce[10], co[10], de[10], dO[10], ve[10], vo[10];
-        split(cc, ce, co); split(dd, de, dO);
-#pragma unroll
-        for (int k = 0; k < 10; ++k) {
-            ve[k] = pe[k] + 3u * ce[k] + de[k];     // <= 8 * 255 per 16-bit lane
-            vo[k] = po[k] + 3u * co[k] + dO[k];
-            pe[k] = ce[k] + 3u * de[k];
-            po[k] = co[k] + 3u * dO[k];
+}
+__device__ __forceinline__ void bulkLoad(void* smemDst, const void* gmemSrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smemAddr(smemDst)), "l"(gmemSrc), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(160) k_cubic_rgba_tma(DevLevel dst, DevLevel src, Box r) {
+    extern __shared__ __align__(128) unsigned char tmaSmem[];
+    uint32_t (*ring)[2][TMA_ROW_TEXELS] = reinterpret_cast<uint32_t (*)[2][TMA_ROW_TEXELS]>(tmaSmem);
+    __shared__ __align__(8) uint64_t full[TMA_STAGES], empty[TMA_STAGES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sw = src.w, sh = src.h;
+    const int x0 = ((r.minx >> 2) << 2) + blockIdx.x * TMA_STRIP;     // first destination column of the strip
+    const int yb = r.miny + blockIdx.y * TMA_ROWS, ye = min(yb + TMA_ROWS, r.maxy);
+    const int c0 = max(2 * x0 - 4, 0);                                // first staged source column (16-byte aligned)
+    const int nPairs = (ye - yb) + 1;                                 // pair 0 = rows (2yb-1, 2yb), pair k = (2(yb+k-1)+1, +2)
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < TMA_STAGES; ++k) { mbarInit(&full[k], 1); mbarInit(&empty[k], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 4) {
+        // ---------------- producer: one elected lane streams the row pairs of the strip into the ring
+        if (lane == 0) {
+            // bytes of a staged row: up to the end of the source row (whole 16-byte units)
+            const uint32_t bytes = (uint32_t)min(TMA_ROW_BYTES, ((sw - c0) * 4 + 15) & ~15);
+            for (int k = 0; k < nPairs; ++k) {
+                const int st = k % TMA_STAGES;
+                if (k >= TMA_STAGES) mbarWait(&empty[st], ((k / TMA_STAGES) - 1) & 1);
+                const int ra = k == 0 ? 2 * yb - 1 : 2 * (yb + k - 1) + 1, rb = ra + 1;
+                mbarExpectTx(&full[st], 2 * bytes);
+                bulkLoad(&ring[st][0][0], rowPtr<uint32_t>(src, max(0, min(ra, sh - 1))) + c0, bytes, &full[st]);
+                bulkLoad(&ring[st][1][0], rowPtr<uint32_t>(src, max(0, min(rb, sh - 1))) + c0, bytes, &full[st]);
+            }
         }
-        // outer columns from the neighbouring lanes where they hold them
-        const uint32_t lE = __shfl_up_sync(full, ve[8], 1), lO = __shfl_up_sync(full, vo[8], 1);
-        const uint32_t rE = __shfl_down_sync(full, ve[1], 1), rO = __shfl_down_sync(full, vo[1], 1);
-        if (leftOk) { ve[0] = lE; vo[0] = lO; }
-        if (rightOk) { ve[9] = rE; vo[9] = rO; }
-        if (!active) continue;
-        uint32_t o[4];
+        return;
+    }
+
+    // ---------------- consumers: thread = two destination texels x, x + 1 (source columns 2x-1 .. 2x+4)
+    const int t = threadIdx.x;                                        // 0 .. 127
+    const int x = x0 + 2 * t;
+    const bool active = x < r.maxx && 2 * x < sw && x + 1 >= r.minx;
+    // staged-row indices of the six source columns (clamped to the image: mipmap.d:915-935)
+    int ci[6];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            // destination x+t: columns 2(x+t)-1 .. 2(x+t)+2 = indices 2t .. 2t+3; the right-most tap is clamped to the
-            // last source column (mipmap.d:934-935)
-            uint32_t e3 = ve[2 * t + 3], o3 = vo[2 * t + 3];
-            if (2 * (x + t) + 2 > sw - 1) { e3 = ve[2 * t + 2]; o3 = vo[2 * t + 2]; }
-            const uint32_t sl = (ve[2 * t] + e3) + 3u * (ve[2 * t + 1] + ve[2 * t + 2]) + 0x00200020u;
-            const uint32_t sh2 = (vo[2 * t] + o3) + 3u * (vo[2 * t + 1] + vo[2 * t + 2]) + 0x00200020u;
-            o[t] = ((sl >> 6) & 0x00ff00ffu) | (((sh2 >> 6) & 0x00ff00ffu) << 8);
+    for (int k = 0; k < 6; ++k) ci[k] = max(0, min(2 * x - 1 + k, sw - 1)) - c0;
+    const bool vec = active && 2 * x + 3 <= sw - 1;                   // columns 2x .. 2x+3 as one 128-bit shared load
+    auto readRow = [&](const uint32_t* row, uint32_t (&e)[6], uint32_t (&o)[6]) {
+        uint32_t v[6];
+        if (vec) {
+            const uint4 q = *reinterpret_cast<const uint4*>(row + ci[1]);
+            v[0] = row[ci[0]]; v[1] = q.x; v[2] = q.y; v[3] = q.z; v[4] = q.w; v[5] = row[ci[5]];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v[k] = row[ci[k]];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { e[k] = evenBytes(v[k]); o[k] = oddBytes(v[k]); }
+    };
+    uint32_t pe[6], po[6];
+    for (int k = 0; k < nPairs; ++k) {
+        const int st = k % TMA_STAGES;
+        mbarWait(&full[st], (k / TMA_STAGES) & 1);
+        uint32_t ce[6], co[6], de[6], dO[6];
+        if (active) { readRow(ring[st][0], ce, co); readRow(ring[st][1], de, dO); }
+        __syncwarp();
+        if (lane == 0) mbarArrive(&empty[st]);                        // this warp is done with the stage
+        if (!active) continue;
+        if (k == 0) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { pe[c] = ce[c] + 3u * de[c]; po[c] = co[c] + 3u * dO[c]; }
+            continue;
+        }
+        const int y = yb + k - 1;
+        uint32_t ve[6], vo[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            ve[c] = pe[c] + 3u * ce[c] + de[c];                       // <= 8 * 255 per 16-bit lane
+            vo[c] = po[c] + 3u * co[c] + dO[c];
+            pe[c] = ce[c] + 3u * de[c];
+            po[c] = co[c] + 3u * dO[c];
+        }
+        uint32_t o[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            // destination x+u: columns 2(x+u)-1 .. 2(x+u)+2 = indices 2u .. 2u+3 (already clamped through ci[])
+            const uint32_t sl = (ve[2 * u] + ve[2 * u + 3]) + 3u * (ve[2 * u + 1] + ve[2 * u + 2]) + 0x00200020u;
+            const uint32_t sh2 = (vo[2 * u] + vo[2 * u + 3]) + 3u * (vo[2 * u + 1] + vo[2 * u + 2]) + 0x00200020u;
+            o[u] = ((sl >> 6) & 0x00ff00ffu) | (((sh2 >> 6) & 0x00ff00ffu) << 8);
         }
         uint32_t* dp = rowPtrW<uint32_t>(dst, y);
-        if (x >= r.minx && x + 3 < r.maxx) *reinterpret_cast<uint4*>(dp + x) = make_uint4(o[0], o[1], o[2], o[3]);
+        if (x >= r.minx && x + 1 < r.maxx) *reinterpret_cast<uint2*>(dp + x) = make_uint2(o[0], o[1]);
         else {
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-                if (x + t >= r.minx && x + t < r.maxx) dp[x + t] = o[t];
+            if (x >= r.minx && x < r.maxx) dp[x] = o[0];
+            if (x + 1 >= r.minx && x + 1 < r.maxx) dp[x + 1] = o[1];
         }
-    }
     }
 }
 
@@ -528,13 +560,16 @@ void launch_box_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_
     k_box_l16<<<gridFor(quads, r.maxy - r.miny, block), block, 0, s>>>(dst, src, r);
 }
 void launch_cubic_rgba(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s) {
-    static const int walkOn = getenv("B2_CUBIC_WALK") ? atoi(getenv("B2_CUBIC_WALK")) : 1;   // tuning aid (0: never)
-    {   // large rectangles: walking warps, when there are enough of them to fill the GPU (8 per SM; measured on the 8192^2
-        // pyramid: 4096^2 -> 2048^2 in 18.1 us against 21.2 us; 8-row walks on 2048^2 -> 1024^2 were slower, 9.2 vs 8.2 us)
+    static const int tmaOn = getenv("B2_CUBIC_TMA") ? atoi(getenv("B2_CUBIC_TMA")) : 1;      // tuning aid (0: never, 2: always — tests)
+    {   // large rectangles: the TMA-fed strip walker, when its CTAs fill the GPU
         const int x0 = (r.minx >> 2) << 2;
-        const int strips = (r.maxx - x0 + 127) / 128, rows = r.maxy - r.miny;
-        if (walkOn && (long long)strips * ((rows + 15) / 16) >= 148 * 8) {
-            k_cubic_rgba_walk<16><<<dim3((strips + 3) / 4, (rows + 15) / 16), 128, 0, s>>>(dst, src, r);
+        const int strips = (r.maxx - x0 + TMA_STRIP - 1) / TMA_STRIP, chunks = (r.maxy - r.miny + TMA_ROWS - 1) / TMA_ROWS;
+        static const long long minCtas = getenv("B2_CUBIC_TMA_MIN") ? atoll(getenv("B2_CUBIC_TMA_MIN")) : 148 * 2;
+        if (tmaOn && ((long long)strips * chunks >= minCtas || tmaOn == 2) && r.maxx > r.minx && r.maxy > r.miny) {
+            static bool attr = false;
+            const size_t smem = sizeof(uint32_t) * TMA_STAGES * 2 * TMA_ROW_TEXELS;
+            if (!attr) { cudaFuncSetAttribute(k_cubic_rgba_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+            k_cubic_rgba_tma<<<dim3(strips, chunks), 160, smem, s>>>(dst, src, r);
             return;
         }
     }
