@@ -55,6 +55,8 @@ SIGNATURES = {
     "b2mip_generate_chain": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "b2mip_generate_levels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), box2i, C.POINTER(box2i)]),
     "b2_set_mip_fusion": (C.c_int, [C.c_int]),
+    "b2_set_mip_wave": (C.c_int, [C.c_int]),
+    "b2_mip_wave_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), box2i, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
     "b2_dirty_rects_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "b2_dirty_rects_destroy": (None, [C.c_void_p]),
     "b2_dirty_rects_add": (C.c_int, [C.c_void_p, box2i]),

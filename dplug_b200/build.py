@@ -19,6 +19,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-ftz=false",
 UNITS = [
     ("b2pbr.cu", ["-fmad=false"]),
     ("mip_kernels.cu", ["-fmad=false"] + ["-D%s=%s" % (k, os.environ[k]) for k in ("B2_TMA_ROWS", "B2_TMA_STAGES") if k in os.environ]),
+    ("mip_wave.cu", ["-fmad=false"] + ["-D%s=%s" % (k, os.environ[k]) for k in ("B2_WAVE_MIN_CTAS", "B2_WAVE_UNROLL", "B2_WAVE_ITEM_TEXELS") if k in os.environ]),
     ("mip_fused.cu", ["-fmad=false"] + (["-DB2_MIP_DEBUG"] if os.environ.get("B2_MIP_DEBUG") else [])),
     ("pbr_exact.cu", ["-fmad=false"]),
     ("pbr_tex.cu", ["-DB2_TEX_MIN_CTAS=%s" % os.environ.get("B2_TEX_MIN_CTAS", "5")]),

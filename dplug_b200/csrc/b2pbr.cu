@@ -15,6 +15,7 @@
 #include "../../include/b2pbr.h"
 #include "common.cuh"
 #include "host_rects.hpp"
+#include "mip_wave.hpp"
 
 namespace b2 {
 // kernels (mip_kernels.cu, mip_fused.cu, pbr_exact.cu, pbr_tex.cu)
@@ -74,6 +75,17 @@ struct b2mip {
     // every level as a pitch-2D texture object over the same memory (linear filter, clamp addressing, unnormalised
     // coordinates, normalised-float reads): the lighting kernel's bilinear samplers run on the texture units
     std::vector<cudaTextureObject_t> tex;
+    // plans of the whole-pyramid wavefront kernel (mip_wave.cu): item list + counters on the device, re-used while the
+    // caller regenerates the same chain (a full redraw never changes it)
+    struct WavePlan {
+        std::vector<int> key;
+        WaveItem* dItems = nullptr; WaveItem* hItems = nullptr; int cap = 0, nItems = 0;
+        int* dCtl = nullptr; int ctlCap = 0, nCtl = 0;
+        cudaStream_t lastStream = nullptr; bool usedOnce = false, pinned = false;
+        uint64_t used = 0;
+    };
+    std::vector<WavePlan> wavePlans;
+    uint64_t waveClock = 0;
 };
 
 // A pitched host<->device copy is executed row by row by the copy engine (measured: 2 MB of 2480-byte rows take 160 us
@@ -314,6 +326,97 @@ static int mipGenerateGroup(b2mip* m, int first, int n, const int* q, const b2_b
     return B2_OK;
 }
 
+// ---- whole chain in one persistent launch (mip_wave.cu), for chains that start on a large level (the regime where the
+// levels otherwise stream one launch each).  OFF by default: measured on the B200 it moves the minimum of bytes (8192^2
+// pyramid: 269 MB read + 71 MB written per chain, level l + 1 reads level l from L2) but is slower than the launches it
+// replaces (131 - 152 us against 98 us; 3840x2160 diffuse chain 38 - 48 us against 25 us): every level adds a
+// claim / wait / compute / release hop to the tail and the software queue costs more per item than the hardware block
+// scheduler (profiles/r2_mip_wave.md).  b2_set_mip_wave(1) / B2_MIP_WAVE=1 switch it on.  `*launched` tells whether the
+// chain was enqueued; when it was not (knob off, row bands, plan not yet on the device while a graph is being recorded)
+// the caller falls back to the per-level / fused launches, which write the same bytes.
+// (Also measured and removed: the per-level kernels cut into 2 - 8 row chunks on one stream per level with events, so
+// that the ALU-bound cubic levels run beside the HBM-bound level-1 box: 106 - 130 us against 98 us.)
+static int g_mipWave = getenv("B2_MIP_WAVE") ? atoi(getenv("B2_MIP_WAVE")) : 0;
+static int g_mipWaveSteps = getenv("B2_MIP_WAVE_STEPS") ? atoi(getenv("B2_MIP_WAVE_STEPS")) : kWaveMaxSteps;                   // tuning aid: at most this many levels per wavefront launch
+static long long g_mipWaveTail = getenv("B2_MIP_WAVE_TAIL") ? atoll(getenv("B2_MIP_WAVE_TAIL")) : 0;                           // levels whose source has at most this many texels are left to the fused launches
+static long long g_mipWaveAbove = getenv("B2_MIP_WAVE_ABOVE") ? atoll(getenv("B2_MIP_WAVE_ABOVE")) : (1ll << 20);
+
+static int mipGenerateWave(b2mip* m, int first, int n, const int* q, const b2_box2i* rects, bool* launched) {
+    *launched = false;
+    if (!g_mipWave || n < 2 || n > kWaveMaxSteps) return B2_OK;
+    if (m->levels[0].rows != m->H) return B2_OK;                                   // row bands keep their own schedule
+    // only where the levels would otherwise stream one launch each (not below the fused kernel's regime, b2_set_mip_fusion)
+    const long long above = g_mipWaveAbove > g_mipFuseBelow ? g_mipWaveAbove : g_mipFuseBelow;
+    if (boxW(rects[0]) <= 0 || boxH(rects[0]) <= 0 || 4ll * boxW(rects[0]) * boxH(rects[0]) <= above) return B2_OK;
+    const bool rgba = m->color == B2_COLOR_RGBA8;
+    Box upd[kWaveMaxSteps];
+    for (int k = 0; k < n; ++k) {
+        if (!rgba && q[k] == B2_QUALITY_BOX_ALPHACOV_PREMUL) return fail(B2_ERR_INVALID, "generateLevel: boxAlphaCovIntoPremul is RGBA-only (mipmap.d:594-595)");
+        if (q[k] < 0 || q[k] > 2) return fail(B2_ERR_INVALID, "generateLevel: unknown quality");
+        const b2_box2i& r = rects[k];
+        if (boxW(r) <= 0 || boxH(r) <= 0) { upd[k] = Box{0, 0, 0, 0}; continue; }   // a no-op in the reference
+        if (int rc = mipCheckRect(m, first + k, r, "generateLevel")) return rc;
+        upd[k] = toBox(r);
+    }
+    CU(cudaSetDevice(m->device));
+    std::vector<int> key;
+    key.reserve(2 + 5 * n);
+    key.push_back(first); key.push_back(n);
+    for (int k = 0; k < n; ++k) { key.push_back(q[k]); key.push_back(upd[k].minx); key.push_back(upd[k].miny); key.push_back(upd[k].maxx); key.push_back(upd[k].maxy); }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CU(cudaStreamIsCapturing(m->stream, &cap));
+    const bool capturing = cap != cudaStreamCaptureStatusNone;
+    b2mip::WavePlan* plan = nullptr;
+    for (auto& wp : m->wavePlans)
+        if (wp.key == key) { plan = &wp; break; }
+    if (!plan) {
+        if (capturing) return B2_OK;   // the plan has to be uploaded outside a capture: this recording takes the per-level launches
+        std::vector<WaveItem> items;
+        int nCtl = 0;
+        DevLevel lv[kWaveMaxSteps + 1];
+        for (int k = 0; k <= n; ++k) lv[k] = m->levels[first - 1 + k];
+        if (wave_build_plan(lv, upd, q, n, rgba, items, &nCtl) != 0 || items.empty()) return B2_OK;
+        // slot: a free one (up to 8), else the least recently used that no graph refers to
+        if (m->wavePlans.size() < 8) { m->wavePlans.emplace_back(); plan = &m->wavePlans.back(); }
+        else {
+            for (auto& wp : m->wavePlans)
+                if (!wp.pinned && (!plan || wp.used < plan->used)) plan = &wp;
+            if (!plan) { m->wavePlans.emplace_back(); plan = &m->wavePlans.back(); }
+        }
+        if (plan->usedOnce) CU(cudaStreamSynchronize(plan->lastStream));            // its last launch and upload are over
+        const int nItems = (int)items.size();
+        if (nItems > plan->cap) {
+            if (plan->dItems) cudaFree(plan->dItems);
+            if (plan->hItems) cudaFreeHost(plan->hItems);
+            plan->dItems = nullptr; plan->hItems = nullptr;
+            plan->cap = nItems + nItems / 2 + 256;
+            CU(cudaMalloc((void**)&plan->dItems, sizeof(WaveItem) * plan->cap));
+            CU(cudaMallocHost((void**)&plan->hItems, sizeof(WaveItem) * plan->cap));
+        }
+        if (nCtl > plan->ctlCap) {
+            if (plan->dCtl) cudaFree(plan->dCtl);
+            plan->dCtl = nullptr;
+            plan->ctlCap = nCtl + nCtl / 2 + 64;
+            CU(cudaMalloc((void**)&plan->dCtl, sizeof(int) * plan->ctlCap));
+            CU(cudaMemsetAsync(plan->dCtl, 0, sizeof(int) * plan->ctlCap, m->stream));   // the kernel leaves them zero
+        }
+        memcpy(plan->hItems, items.data(), sizeof(WaveItem) * nItems);
+        CU(cudaMemcpyAsync(plan->dItems, plan->hItems, sizeof(WaveItem) * nItems, cudaMemcpyHostToDevice, m->stream));
+        plan->key = key; plan->nItems = nItems; plan->nCtl = nCtl;
+    }
+    if (capturing) plan->pinned = true;                                             // a recorded graph replays this plan
+    plan->used = ++m->waveClock; plan->usedOnce = true; plan->lastStream = m->stream;
+    WaveArgs a{};
+    for (int k = 0; k <= n; ++k) a.lv[k] = m->levels[first - 1 + k];
+    for (int k = 0; k < n; ++k) a.upd[k] = upd[k];
+    a.items = plan->dItems; a.nItems = plan->nItems; a.ctl = plan->dCtl; a.nCtl = plan->nCtl; a.nz = 0x8000000080000000ull;
+    launch_mip_wave(a, m->stream);
+    m->launches++;
+    CU(cudaGetLastError());
+    *launched = true;
+    return B2_OK;
+}
+
 // levels first .. first + n - 1, in launches of up to three levels (or level by level with fusion off); row bands
 // take the same launches (the fused kernel clips its regions to the rows a band stores)
 static int mipGenerateLevels(b2mip* m, int first, int n, const int* q, const b2_box2i* rects, bool fuseAll = false) {
@@ -325,7 +428,17 @@ static int mipGenerateLevels(b2mip* m, int first, int n, const int* q, const b2_
         }
         return B2_OK;
     }
-    for (int k = 0; k < n;) {
+    int k0 = 0;
+    if (!fuseAll) {
+        // the wavefront launch takes the large levels (those that would stream one launch each); the small levels that
+        // follow are latency: they stay with the fused launches
+        int nw = 0;
+        while (nw < n && nw < g_mipWaveSteps && boxW(rects[nw]) > 0 && boxH(rects[nw]) > 0 && 4ll * boxW(rects[nw]) * boxH(rects[nw]) > g_mipWaveTail) ++nw;
+        bool launched = false;
+        if (int rc = mipGenerateWave(m, first, nw, q, rects, &launched)) return rc;
+        if (launched) k0 = nw;
+    }
+    for (int k = k0; k < n;) {
         // Large updates are bandwidth work and the lean one-launch-per-level kernels stream them best (measured: the
         // fused kernel's region bookkeeping costs more issue slots than the saved HBM round trip is worth once a step
         // reads ~1 M texels).  Small updates — small levels, or dirty rectangles of large ones — are launch latency:
@@ -368,6 +481,12 @@ void b2mip_destroy(b2mip* m) {
     for (cudaTextureObject_t t : m->tex) if (t) cudaDestroyTextureObject(t);
     if (m->alloc) cudaFree(m->alloc);
     if (m->staging) cudaFree(m->staging);
+    for (auto& wp : m->wavePlans) {
+        if (wp.usedOnce && wp.lastStream != m->stream) cudaStreamSynchronize(wp.lastStream);
+        if (wp.dItems) cudaFree(wp.dItems);
+        if (wp.hItems) cudaFreeHost(wp.hItems);
+        if (wp.dCtl) cudaFree(wp.dCtl);
+    }
     if (m->ownStream && m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -482,6 +601,32 @@ int b2_set_mip_fusion(int enabled) {
     const int was = g_mipFusion ? (g_mipFuseBelow >= (1ll << 40) ? 2 : 1) : 0;
     g_mipFusion = enabled != 0;
     g_mipFuseBelow = enabled == 2 ? (1ll << 40) : (getenv("B2_MIP_FUSE_BELOW") ? atoll(getenv("B2_MIP_FUSE_BELOW")) : (1ll << 20));
+    return was;
+}
+int b2_mip_wave_plan(int color, int w, int h, int first_level, int n, const int* qualities, b2_box2i prev, int* items8, int cap_items, int* n_ctl) {
+    if (n < 1 || n > kWaveMaxSteps || !qualities || first_level < 1 || w < 1 || h < 1) return fail(B2_ERR_INVALID, "b2_mip_wave_plan: bad arguments");
+    DevLevel lv[kWaveMaxSteps + 1];
+    Box upd[kWaveMaxSteps];
+    for (int k = 0; k <= n; ++k) {
+        const int l = first_level - 1 + k;
+        lv[k] = DevLevel{nullptr, 0, w >> l, h >> l, 0, h >> l};
+        if (k > 0 && (lv[k].w < 1 || lv[k].h < 1)) return fail(B2_ERR_INVALID, "b2_mip_wave_plan: level out of range");
+    }
+    for (int k = 0; k < n; ++k) {
+        prev = impactOnNextLevel(qualities[k], prev, lv[k].w, lv[k].h);
+        upd[k] = (boxW(prev) > 0 && boxH(prev) > 0) ? toBox(prev) : Box{0, 0, 0, 0};
+    }
+    std::vector<WaveItem> items;
+    int nCtl = 0;
+    if (wave_build_plan(lv, upd, qualities, n, color == B2_COLOR_RGBA8, items, &nCtl) != 0) return fail(B2_ERR_STATE, "b2_mip_wave_plan: chain cannot be planned");
+    if (n_ctl) *n_ctl = nCtl;
+    if (items8)
+        for (size_t i = 0; i < items.size() && (int)i < cap_items; ++i) memcpy(items8 + 8 * i, &items[i], sizeof(WaveItem));
+    return (int)items.size();
+}
+int b2_set_mip_wave(int enabled) {
+    const int was = g_mipWave;
+    g_mipWave = enabled != 0;
     return was;
 }
 int b2mip_sample(b2mip* m, int kind, int n, const float* level, const float* x, const float* y, float* out4) {

@@ -110,6 +110,17 @@ int b2mip_generate_levels(b2mip*, int first_level, int n, const int* qualities, 
 /* tuning / debugging knob (process-wide): 0 = every generateLevel is its own launch; 1 (default) = levels whose source
  * has at most 2^20 texels are fused, larger ones stream level by level; 2 = fuse everything.  Returns the previous setting. */
 int b2_set_mip_fusion(int enabled);
+/* experiment knob (process-wide): 1 = a chain of two or more levels that starts on a large level (more than 2^20 source
+ * texels; unbanded objects) runs as ONE persistent launch in which the levels advance together down the image
+ * (csrc/mip_wave.cu: DRAM traffic at the algorithmic minimum, but measured slower than the per-level launches on the
+ * B200); 0 (default) = never.  Same bytes either way.  Returns the previous setting. */
+int b2_set_mip_wave(int enabled);
+/* host only (no GPU needed; test hook): the work list of that launch for the chain b2mip_generate_levels(first_level, n,
+ * qualities, update_rect_previous_level) would run on a w x h pyramid.  Writes up to cap_items items of 8 ints each
+ * {step | kind << 16, block_row, block_col_begin, block_col_end, dep_lo, dep_hi, dep_target, done_counter} in launch
+ * order, the number of control words to *n_ctl, and returns the number of items (negative: B2_ERR_*). */
+int b2_mip_wave_plan(int color, int w, int h, int first_level, int n, const int* qualities, b2_box2i update_rect_previous_level,
+                     int* items8, int cap_items, int* n_ctl);
 /* the three samplers, evaluated on the device for `n` query points (test hook for mipmap.d:149-496) */
 int b2mip_sample(b2mip*, int kind /*0 linear,1 cubic,2 linearMipmap*/, int n, const float* level, const float* x,
                  const float* y, float* out4);

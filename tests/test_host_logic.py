@@ -64,7 +64,7 @@ def test_exact_mip_kernels_contain_no_fused_multiply_add(b2):
     import subprocess
     if not shutil.which("cuobjdump"):
         pytest.skip("cuobjdump not on PATH")
-    for obj in ("mip_kernels.o", "mip_fused.o"):
+    for obj in ("mip_kernels.o", "mip_fused.o", "mip_wave.o"):
         path = os.path.join(ROOT, "dplug_b200", "build", obj)
         if not os.path.exists(path):
             pytest.skip("objects not kept (library built elsewhere)")
