@@ -293,6 +293,28 @@ class PBRCompositor:
                                          window.shape[0], userOrigin[0], userOrigin[1], _lib.boxes(rects), len(rects), 1 if redrawBorders else 0))
         return window
 
+    # --- screenshot encoders (gui/dplug/gui/screencap.d:21-136) on the rendered buffer of doDraw stage G.bis -------
+    def encodeScreenshotAsQB(self, pixelFormat):
+        """encodeScreenshotAsQB (screencap.d:21-84): the .qb voxel file (W x 26 x H voxels) as bytes."""
+        n = int(self._l.b2pbr_screenshot_qb_size(self._h))
+        buf = np.empty(n, dtype=np.uint8)
+        _lib.check(self._l.b2pbr_screenshot_qb(self._h, pixelFormat, buf.ctypes.data_as(C.c_void_p), n))
+        return buf.tobytes()
+
+    def screenshotPixels(self, pixelFormat):
+        """the image encodeScreenshotAsPNG hands to its encoder (screencap.d:88-131): (h, w, 4) uint8, RGBA"""
+        out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        _lib.check(self._l.b2pbr_screenshot_rgba(self._h, pixelFormat, out.ctypes.data_as(C.c_void_p), out.strides[0]))
+        return out
+
+    def encodeScreenshotAsPNG(self, pixelFormat):
+        """encodeScreenshotAsPNG (screencap.d:88-136): a PNG file as bytes."""
+        n = int(self._l.b2pbr_screenshot_png_size(self._h))
+        buf = np.empty(n, dtype=np.uint8)
+        written = C.c_size_t(0)
+        _lib.check(self._l.b2pbr_screenshot_png(self._h, pixelFormat, buf.ctypes.data_as(C.c_void_p), n, C.byref(written)))
+        return buf[: written.value].tobytes()
+
     def sync(self):
         _lib.check(self._l.b2pbr_sync(self._h))
 

@@ -31,6 +31,7 @@ void launch_copy_diffuse(const DevLevel& dst, const DevLevel& src, const Box* bo
 void launch_swizzle(const DevLevel& dst, const DevLevel& src, Box box, int pf, cudaStream_t s);
 void launch_layer(bool blend, const DevLevel* dst3, const DevLevel* src3, const DevLevel* op3, Box box, int px, int py, cudaStream_t s);
 void launch_present(const DevLevel& win, const DevLevel& src, Box box, int dx, int dy, int pf, const uint8_t* lut, cudaStream_t s);
+void launch_screenshot_qb(uint32_t* vox, const DevLevel& src, const DevLevel& depth, int W, int H, int pf, const uint8_t* lut, cudaStream_t s);
 void launch_fill32(const DevLevel& win, uint32_t value, cudaStream_t s);
 void launch_pbr_exact(const PbrArgs& args, int gridBlocks, cudaStream_t stream);
 constexpr int kQuadrantRows = 32;   // rows of a full-height warp quadrant of k_pbr_tex (CTA box = 64 x 64)
@@ -2015,6 +2016,124 @@ int b2pbr_present(b2pbr* c, int pf, void* window, size_t window_pitch, int windo
                                  (size_t)boxW(r) * 4, (size_t)boxH(r), cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
+// ---- screenshot encoders (gui/dplug/gui/screencap.d:21-136), taken where doDraw takes them: on the
+// rendered buffer of stage G.bis (graphics.d:848-857), i.e. the composited frame after the colour-correction tables and
+// reorderComponents(pf).
+static const size_t kQbHeader = 50;
+size_t b2pbr_screenshot_qb_size(const b2pbr* c) {
+    return (c && c->outAlloc) ? kQbHeader + (size_t)c->W * 26 * (size_t)c->H * 4 : 0;
+}
+int b2pbr_screenshot_qb(b2pbr* c, int pf, void* out, size_t cap) {
+    if (!c || !c->outAlloc || !out || pf < 0 || pf > 2) return fail(B2_ERR_INVALID, "screenshot_qb: bad arguments");
+    if (c->banded) return fail(B2_ERR_STATE, "screenshot: not available on a row band");
+    const size_t voxBytes = (size_t)c->W * 26 * (size_t)c->H * 4;
+    if (cap < kQbHeader + voxBytes) return fail(B2_ERR_INVALID, "screenshot_qb: buffer smaller than b2pbr_screenshot_qb_size()");
+    CU(cudaSetDevice(c->device));
+    uint8_t* o = (uint8_t*)out;
+    size_t n = 0;
+    auto put8 = [&](uint8_t v) { o[n++] = v; };
+    auto put32 = [&](uint32_t v) { for (int k = 0; k < 4; ++k) put8((uint8_t)(v >> (8 * k))); };
+    put8(1); put8(1); put8(0); put8(0);                    // .qb version 1.1.0.0 (screencap.d:33-36)
+    put32(0); put32(0); put32(0); put32(0); put32(1);      // RGBA, left handed, uncompressed, alpha = visibility, one matrix
+    put8(1); put8('0');                                    // matrix name "0"
+    put32((uint32_t)c->W); put32(26u); put32((uint32_t)c->H);
+    put32(0); put32(0); put32(0);                          // position
+    uint32_t* dVox = nullptr;
+    CU(cudaMalloc((void**)&dVox, voxBytes));
+    launch_screenshot_qb(dVox, c->out, c->depth->levels[0], c->W, c->H, pf, c->lutOn ? c->dLut : nullptr, c->stream);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(o + kQbHeader, dVox, voxBytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dVox);
+    CU(e);
+    return B2_OK;
+}
+// the pixel pass of encodeScreenshotAsPNG (screencap.d:88-131): the rendered buffer brought back from the window's pixel
+// format to RGBA.  Re-ordering to `pf` and back is the identity on the colour channels and the alpha written by
+// reorderComponents is 255 in every format, so the result does not depend on `pf`: colour-corrected r, g, b, 255.
+int b2pbr_screenshot_rgba(b2pbr* c, int pf, void* out_rgba, size_t pitch) {
+    if (!c || !c->outAlloc || !out_rgba || pf < 0 || pf > 2 || pitch < (size_t)c->W * 4) return fail(B2_ERR_INVALID, "screenshot_rgba: bad arguments");
+    if (c->banded) return fail(B2_ERR_STATE, "screenshot: not available on a row band");
+    CU(cudaSetDevice(c->device));
+    DevLevel tmp = c->out;
+    uint8_t* d = nullptr;
+    CU(cudaMalloc((void**)&d, (size_t)tmp.pitch * c->H));
+    tmp.base = d;
+    launch_present(tmp, c->out, Box{0, 0, c->W, c->H}, 0, 0, B2_PF_RGBA8, c->lutOn ? c->dLut : nullptr, c->stream);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(out_rgba, pitch, d, (size_t)tmp.pitch, (size_t)c->W * 4, (size_t)c->H, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    CU(e);
+    return B2_OK;
+}
+// encodeScreenshotAsPNG: the pixels above in a PNG container (8-bit RGBA, filter 0, deflate "stored" blocks — gamut's
+// encoder is an un-vendored dependency and PNG bytes are not canonical; any decoder returns the reference's pixels).
+static uint32_t crc32Update(uint32_t crc, const uint8_t* p, size_t n) {
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t v = i;
+            for (int k = 0; k < 8; ++k) v = (v & 1) ? 0xEDB88320u ^ (v >> 1) : v >> 1;
+            table[i] = v;
+        }
+        init = true;
+    }
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+    return crc;
+}
+size_t b2pbr_screenshot_png_size(const b2pbr* c) {
+    if (!c || !c->outAlloc) return 0;
+    const size_t raw = ((size_t)c->W * 4 + 1) * (size_t)c->H, blocks = (raw + 65534) / 65535;
+    return 8 + 25 + (12 + 2 + raw + 5 * blocks + 4) + 12;
+}
+int b2pbr_screenshot_png(b2pbr* c, int pf, void* out, size_t cap, size_t* written) {
+    if (!c || !c->outAlloc || !out) return fail(B2_ERR_INVALID, "screenshot_png: bad arguments");
+    const size_t need = b2pbr_screenshot_png_size(c);
+    if (cap < need) return fail(B2_ERR_INVALID, "screenshot_png: buffer smaller than b2pbr_screenshot_png_size()");
+    const size_t rowBytes = (size_t)c->W * 4 + 1, raw = rowBytes * (size_t)c->H;
+    std::vector<uint8_t> px(raw);
+    if (int rc = b2pbr_screenshot_rgba(c, pf, px.data() + 1, rowBytes)) return rc;   // byte 0 of every scanline: filter type 0
+    for (int y = 0; y < c->H; ++y) px[(size_t)y * rowBytes] = 0;
+    uint8_t* o = (uint8_t*)out;
+    size_t n = 0;
+    auto be32 = [&](uint32_t v) { o[n++] = (uint8_t)(v >> 24); o[n++] = (uint8_t)(v >> 16); o[n++] = (uint8_t)(v >> 8); o[n++] = (uint8_t)v; };
+    auto chunk = [&](const char* type, const uint8_t* data, size_t len) {
+        be32((uint32_t)len);
+        const size_t start = n;
+        memcpy(o + n, type, 4); n += 4;
+        if (len) { memcpy(o + n, data, len); n += len; }
+        be32(crc32Update(0xffffffffu, o + start, n - start) ^ 0xffffffffu);
+    };
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    memcpy(o, sig, 8); n = 8;
+    uint8_t ihdr[13] = {(uint8_t)(c->W >> 24), (uint8_t)(c->W >> 16), (uint8_t)(c->W >> 8), (uint8_t)c->W,
+                        (uint8_t)(c->H >> 24), (uint8_t)(c->H >> 16), (uint8_t)(c->H >> 8), (uint8_t)c->H, 8, 6, 0, 0, 0};
+    chunk("IHDR", ihdr, 13);
+    std::vector<uint8_t> z;
+    z.reserve(raw + raw / 65535 * 5 + 16);
+    z.push_back(0x78); z.push_back(0x01);
+    uint32_t a = 1, b = 0;                                  // Adler-32 of the raw scanlines
+    for (size_t off = 0; off < raw || off == 0; off += 65535) {
+        const size_t len = raw - off < 65535 ? raw - off : 65535;
+        z.push_back(off + len >= raw ? 1 : 0);            // BFINAL, BTYPE = 00 (stored)
+        z.push_back((uint8_t)len); z.push_back((uint8_t)(len >> 8));
+        z.push_back((uint8_t)~len); z.push_back((uint8_t)(~len >> 8));
+        z.insert(z.end(), px.begin() + off, px.begin() + off + len);
+        for (size_t i = 0; i < len; ++i) { a += px[off + i]; if (a >= 65521) a -= 65521; b += a; if (b >= 65521) b -= 65521; }
+        if (raw == 0) break;
+    }
+    const uint32_t adler = (b << 16) | a;
+    z.push_back((uint8_t)(adler >> 24)); z.push_back((uint8_t)(adler >> 16)); z.push_back((uint8_t)(adler >> 8)); z.push_back((uint8_t)adler);
+    chunk("IDAT", z.data(), z.size());
+    chunk("IEND", nullptr, 0);
+    if (written) *written = n;
     return B2_OK;
 }
 

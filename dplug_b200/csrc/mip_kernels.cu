@@ -213,6 +213,26 @@ __global__ void __launch_bounds__(256) k_present(DevLevel win, DevLevel src, Box
     else o = r | (g << 8) | (b << 16) | 0xff000000u;                // RGBA8
     rowPtrW<uint32_t>(win, j + dy)[i + dx] = o;
 }
+// encodeScreenshotAsQB — gui/dplug/gui/screencap.d:21-84: one column of 26 voxels per pixel of the rendered buffer (the
+// composited pixel after colour correction and reorderComponents(pf): graphics.d:843-857), visible up to
+// 10 + 16 * depth / 65536.  Voxel (x, y, z) is at ((z * 26) + y) * W + x; its colour bytes are bytes 0, 1, 2 of the
+// re-ordered pixel, whatever the window's pixel format (the reference reads them through RGBA's fields).
+__global__ void __launch_bounds__(256) k_screenshot_qb(uint32_t* __restrict__ vox, DevLevel src, DevLevel depth, int W, int H, int pf,
+                                                      const uint8_t* __restrict__ lut) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || z >= H) return;
+    const uint32_t p = __ldg(rowPtr<uint32_t>(src, z) + x);
+    uint32_t r = p & 0xff, g = (p >> 8) & 0xff, b = (p >> 16) & 0xff;
+    if (lut) { r = __ldg(lut + r); g = __ldg(lut + 256 + g); b = __ldg(lut + 512 + b); }
+    uint32_t rgb;
+    if (pf == 1) rgb = b | (g << 8) | (r << 16);          // BGRA8: bytes b, g, r
+    else if (pf == 2) rgb = 0xffu | (r << 8) | (g << 16);  // ARGB8: bytes a (255), r, g
+    else rgb = r | (g << 8) | (b << 16);
+    const int d = 10 + ((16 * (int)__ldg(rowPtr<uint16_t>(depth, z) + x)) >> 16);
+    uint32_t* o = vox + (size_t)z * 26 * W + x;
+#pragma unroll
+    for (int y = 0; y < 26; ++y) o[(size_t)y * W] = rgb | (d >= y ? 0xff000000u : 0u);
+}
 __global__ void __launch_bounds__(256) k_fill32(DevLevel win, uint32_t value) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i < win.w && j < win.h) rowPtrW<uint32_t>(win, j)[i] = value;
@@ -350,6 +370,10 @@ void launch_layer(bool blend, const DevLevel* dst3, const DevLevel* src3, const 
 void launch_present(const DevLevel& win, const DevLevel& src, Box box, int dx, int dy, int pf, const uint8_t* lut, cudaStream_t s) {
     dim3 block(32, 8);
     k_present<<<gridFor(box.maxx - box.minx, box.maxy - box.miny, block), block, 0, s>>>(win, src, box, dx, dy, pf, lut);
+}
+void launch_screenshot_qb(uint32_t* vox, const DevLevel& src, const DevLevel& depth, int W, int H, int pf, const uint8_t* lut, cudaStream_t s) {
+    dim3 block(32, 8);
+    k_screenshot_qb<<<gridFor(W, H, block), block, 0, s>>>(vox, src, depth, W, H, pf, lut);
 }
 void launch_fill32(const DevLevel& win, uint32_t value, cudaStream_t s) {
     dim3 block(32, 8);

@@ -311,6 +311,21 @@ int b2pbr_draw_layer(b2pbr*, b2layer*, int x, int y, const b2_box2i* dirty_rects
  * Raw-layer widget draws between the blit and the re-ordering.  Synchronises. */
 int b2pbr_present(b2pbr*, int pixel_format, void* window, size_t window_pitch, int window_w, int window_h,
                   int user_x, int user_y, const b2_box2i* rects, int n, int redraw_borders);
+/* SURVEY §8(f) row 4 — the screenshot encoders (gui/dplug/gui/screencap.d:21-136), taken where GUIGraphics.doDraw takes
+ * them (stage G.bis, graphics.d:848-857): on the rendered buffer, i.e. the composited frame after the colour-correction
+ * tables and reorderComponents(pixel_format).
+ *  _qb: encodeScreenshotAsQB (screencap.d:21-84) — a .qb voxel file of W x 26 x H voxels built on the device from the
+ *       rendered pixels and level 0 of the depth map; byte-identical to the reference's file.  `cap` must be at least
+ *       b2pbr_screenshot_qb_size().
+ *  _rgba: the pixel pass of encodeScreenshotAsPNG (screencap.d:88-131): the rendered buffer brought back to RGBA.
+ *  _png: those pixels as a PNG file (8-bit RGBA; the reference hands them to the un-vendored `gamut` encoder — PNG bytes
+ *       are not canonical, the decoded image is the reference's).  `cap` >= b2pbr_screenshot_png_size().
+ * All three synchronise. */
+size_t b2pbr_screenshot_qb_size(const b2pbr*);
+int b2pbr_screenshot_qb(b2pbr*, int pixel_format, void* out, size_t cap);
+int b2pbr_screenshot_rgba(b2pbr*, int pixel_format, void* out_rgba, size_t pitch);
+size_t b2pbr_screenshot_png_size(const b2pbr*);
+int b2pbr_screenshot_png(b2pbr*, int pixel_format, void* out, size_t cap, size_t* written);
 /* 3 x 256 transfer tables (red, green, blue) of UIColorCorrection (colorcorrection.d:26-41); NULL = none */
 int b2pbr_set_color_correction(b2pbr*, const uint8_t* rgb_table_768);
 /* setLiftGammaGainContrastRGB (colorcorrection.d:69-116) as a host helper: v = {lift, gamma, gain, contrast} for

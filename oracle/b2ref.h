@@ -67,6 +67,10 @@ int b2ref_gfx_composite_gui(b2ref_gfx*, const b2ref_box2i* rects, int n);
 int b2ref_present(b2ref_imageref composited, b2ref_imageref rendered, int pixel_format, b2ref_imageref window, int user_x, int user_y,
                   const b2ref_box2i* rects, int n, const uint8_t* table768, int redraw_borders);
 
+/* ---- screenshot encoders (gui/dplug/gui/screencap.d:21-136) on the rendered buffer of stage G.bis (graphics.d:848-857) */
+size_t b2ref_screenshot_qb(b2ref_imageref rendered, int pixel_format, b2ref_imageref depth, uint8_t* out, size_t cap);
+int b2ref_screenshot_png_pixels(b2ref_imageref rendered, int pixel_format, uint8_t* out_rgba, size_t out_pitch);
+
 /* ---- widget cache -> level-0 maps: blit (pbrbackgroundgui.d:147-162) or blendWithAlpha (bufferedelement.d:118-131) */
 int b2ref_draw_layer(b2ref_imageref dstD, b2ref_imageref dstZ, b2ref_imageref dstM, b2ref_imageref srcD, b2ref_imageref srcZ,
                      b2ref_imageref srcM, b2ref_imageref opD, b2ref_imageref opZ, b2ref_imageref opM, int x, int y,

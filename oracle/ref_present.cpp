@@ -126,3 +126,48 @@ extern "C" int b2ref_draw_layer(b2ref_imageref dstD, b2ref_imageref dstZ, b2ref_
     }
     return 0;
 }
+
+// ---------------------------------------------------------------- screenshot encoders
+// encodeScreenshotAsQB — gui/dplug/gui/screencap.d:21-84.  `color` is the rendered buffer (after reorderComponents(pf),
+// graphics.d:843-857), read through RGBA's fields: for BGRA8 / ARGB8 windows the "r, g, b" written are simply bytes 0, 1, 2
+// of the re-ordered pixel (the reference does not look at `pf`).  Returns the size of the file; writes at most `cap` bytes.
+extern "C" size_t b2ref_screenshot_qb(b2ref_imageref color, int /*pf*/, b2ref_imageref depth, uint8_t* out, size_t cap) {
+    const int DEPTH = 16, ADD_DEPTH = 10;                  // screencap.d:25-26
+    const int W = color.w, H = color.h;
+    size_t n = 0;
+    auto put8 = [&](uint8_t v) { if (n < cap) out[n] = v; ++n; };
+    auto put32 = [&](uint32_t v) { for (int k = 0; k < 4; ++k) put8((uint8_t)(v >> (8 * k))); };   // writeLE
+    put8(1); put8(1); put8(0); put8(0);                    // .qb version (screencap.d:33-36)
+    put32(0); put32(0); put32(0); put32(0); put32(1);      // RGBA, left handed, uncompressed, visibility mask, one matrix
+    put8(1); put8('0');                                    // matrix name
+    put32((uint32_t)W); put32((uint32_t)(DEPTH + ADD_DEPTH)); put32((uint32_t)H);
+    put32(0); put32(0); put32(0);                          // position
+    for (int z = 0; z < H; ++z) {
+        const uint16_t* depthScan = (const uint16_t*)((const uint8_t*)depth.pixels + (size_t)z * depth.pitch);
+        const uint8_t* colorScan = (const uint8_t*)color.pixels + (size_t)z * color.pitch;
+        for (int y = 0; y < DEPTH + ADD_DEPTH; ++y)
+            for (int x = 0; x < W; ++x) {
+                const int d = ADD_DEPTH + (DEPTH * (int)depthScan[x]) / 65536;
+                put8(colorScan[4 * x + 0]); put8(colorScan[4 * x + 1]); put8(colorScan[4 * x + 2]);
+                put8(d >= y ? 255 : 0);
+            }
+    }
+    return n;
+}
+
+// encodeScreenshotAsPNG, the pixel pass (screencap.d:88-131): a clone of the rendered buffer brought back from the
+// window's pixel format to RGBA; the clone is what the PNG encoder (gamut, un-vendored) receives.
+extern "C" int b2ref_screenshot_png_pixels(b2ref_imageref color, int pf, uint8_t* out_rgba, size_t out_pitch) {
+    for (int y = 0; y < color.h; ++y) {
+        uint8_t* scan = out_rgba + (size_t)y * out_pitch;
+        memcpy(scan, (const uint8_t*)color.pixels + (size_t)y * color.pitch, (size_t)color.w * 4);
+        for (int x = 0; x < color.w; ++x) {
+            if (pf == 1) { uint8_t t = scan[4 * x + 0]; scan[4 * x + 0] = scan[4 * x + 2]; scan[4 * x + 2] = t; }   // BGRA8
+            else if (pf == 2) {                                                                                   // ARGB8
+                const uint8_t a = scan[4 * x + 0], r = scan[4 * x + 1], g = scan[4 * x + 2], b = scan[4 * x + 3];
+                scan[4 * x + 0] = r; scan[4 * x + 1] = g; scan[4 * x + 2] = b; scan[4 * x + 3] = a;
+            }
+        }
+    }
+    return 0;
+}

@@ -69,6 +69,8 @@ def lib():
             "b2ref_gfx_regenerate_mipmaps": (I, [V, C.POINTER(box2i), I]),
             "b2ref_gfx_composite_gui": (I, [V, C.POINTER(box2i), I]),
             "b2ref_draw_layer": (I, [imageref] * 9 + [I, I, C.POINTER(box2i), I, I]),
+            "b2ref_screenshot_qb": (C.c_size_t, [imageref, I, imageref, V, C.c_size_t]),
+            "b2ref_screenshot_png_pixels": (I, [imageref, I, V, C.c_size_t]),
             "b2ref_present": (I, [imageref, imageref, I, imageref, I, I, C.POINTER(box2i), I, V, I]),
             "b2ref_tile_areas": (I, [C.POINTER(box2i), I, I, I, C.POINTER(box2i), I]),
             "b2ref_remove_overlapping_areas": (I, [C.POINTER(box2i), I, C.POINTER(box2i), I]),
@@ -208,6 +210,24 @@ def present(composited, rendered, pixelFormat, window, userOrigin, rects, table=
                              None if t is None else t.ctypes.data_as(C.c_void_p), 1 if redrawBorders else 0)
     assert rc == 0
     return window
+
+
+def encodeScreenshotAsQB(rendered, pixelFormat, depth):
+    """screencap.d:21-84 on host arrays: rendered (h, w, 4) uint8 in the window's pixel format, depth (h, w) uint16"""
+    def ref(a):
+        return imageref(a.shape[1], a.shape[0], a.strides[0], a.ctypes.data)
+    n = lib().b2ref_screenshot_qb(ref(rendered), pixelFormat, ref(depth), None, 0)
+    out = np.empty(n, dtype=np.uint8)
+    assert lib().b2ref_screenshot_qb(ref(rendered), pixelFormat, ref(depth), out.ctypes.data_as(C.c_void_p), n) == n
+    return out.tobytes()
+
+
+def screenshotPixels(rendered, pixelFormat):
+    """the pixel pass of encodeScreenshotAsPNG (screencap.d:88-131)"""
+    out = np.empty_like(rendered)
+    assert lib().b2ref_screenshot_png_pixels(imageref(rendered.shape[1], rendered.shape[0], rendered.strides[0], rendered.ctypes.data), pixelFormat,
+                                             out.ctypes.data_as(C.c_void_p), out.strides[0]) == 0
+    return out
 
 
 def default_params():
