@@ -7,4 +7,5 @@ Host-side mirror (Python, for tests and benchmarks) of the reference interface f
 from ._lib import B2Error, LIB_PATH, box2i, BoxArray  # noqa: F401
 from .mipmap import Mipmap, Quality, RGBA8, L16  # noqa: F401
 from .compositor import PBRCompositor, Layer, default_params, liftGammaGainContrastTable  # noqa: F401
+from .resizer import ImageResizer  # noqa: F401
 from .boxlist import tileAreas, removeOverlappingAreas, impactOnNextLevel, growRect, haveNoOverlap, DirtyRectList  # noqa: F401

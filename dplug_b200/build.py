@@ -22,6 +22,7 @@ UNITS = [
     ("mip_wave.cu", ["-fmad=false"] + ["-D%s=%s" % (k, os.environ[k]) for k in ("B2_WAVE_MIN_CTAS", "B2_WAVE_UNROLL", "B2_WAVE_ITEM_TEXELS") if k in os.environ]),
     ("mip_fused.cu", ["-fmad=false"] + (["-DB2_MIP_DEBUG"] if os.environ.get("B2_MIP_DEBUG") else [])),
     ("pbr_exact.cu", ["-fmad=false"]),
+    ("resizer.cu", ["-fmad=false"]),
     ("pbr_tex.cu", ["-DB2_TEX_MIN_CTAS=%s" % os.environ.get("B2_TEX_MIN_CTAS", "5")]),
 ]
 

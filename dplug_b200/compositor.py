@@ -63,6 +63,13 @@ class Layer:
         _lib.check(self._l.b2layer_upload(self._h, plane, image.ctypes.data_as(C.c_void_p), image.strides[0], _lib.boxes(rects), len(rects)))
 
 
+    def resizePlane(self, plane, kind, image):
+        """ImageResizer into one plane of this device-resident cache (PBRBackgroundGUI.resizeFun,
+        pbrbackgroundgui.d:172-199): `image` is the widget's full-size source, `kind` a resizer.RESIZE_* constant."""
+        image = np.ascontiguousarray(image, dtype=np.uint16 if plane == self.DEPTH else np.uint8)
+        _lib.check(self._l.b2layer_resize_plane(self._h, plane, kind, image.ctypes.data_as(C.c_void_p), image.shape[1], image.shape[0], image.strides[0]))
+
+
 class PBRCompositor:
     """`PBRCompositor(device)`; owns the device twins of the maps GUIGraphics lends to compositeTile."""
 

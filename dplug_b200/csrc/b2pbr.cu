@@ -31,6 +31,7 @@ void launch_copy_diffuse(const DevLevel& dst, const DevLevel& src, const Box* bo
 void launch_swizzle(const DevLevel& dst, const DevLevel& src, Box box, int pf, cudaStream_t s);
 void launch_layer(bool blend, const DevLevel* dst3, const DevLevel* src3, const DevLevel* op3, Box box, int px, int py, cudaStream_t s);
 void launch_present(const DevLevel& win, const DevLevel& src, Box box, int dx, int dy, int pf, const uint8_t* lut, cudaStream_t s);
+int resize_host_to_device(int kind, const void* in, int inW, int inH, size_t inPitch, uint8_t* dOut, size_t outPitch, int outW, int outH, cudaStream_t s);
 void launch_screenshot_qb(uint32_t* vox, const DevLevel& src, const DevLevel& depth, int W, int H, int pf, const uint8_t* lut, cudaStream_t s);
 void launch_fill32(const DevLevel& win, uint32_t value, cudaStream_t s);
 void launch_pbr_exact(const PbrArgs& args, int gridBlocks, cudaStream_t stream);
@@ -768,6 +769,45 @@ int b2layer_upload(b2layer* l, int plane, const void* host, size_t pitch, const 
     // a synchronous copy from pageable memory may return while the DMA from the staging buffer is still in flight;
     // the consumers (b2pbr_draw_layer) run on non-blocking streams that the legacy stream does not order
     CU(cudaStreamSynchronize(cudaStreamLegacy));
+    return B2_OK;
+}
+
+// ---- ImageResizer (resizer.cu)
+static int resizeCheck(int kind, const void* in, int in_w, int in_h, size_t in_pitch, int out_w, int out_h) {
+    if (kind < 0 || kind > 4 || !in || in_w < 1 || in_h < 1 || out_w < 1 || out_h < 1) return fail(B2_ERR_INVALID, "resize: bad arguments");
+    const size_t texel = (kind == B2_RESIZE_DEPTH || kind == B2_RESIZE_GENERIC_L16) ? 2 : 4;
+    if (in_pitch < (size_t)in_w * texel) return fail(B2_ERR_INVALID, "resize: input pitch smaller than a row");
+    if (in_h > 65535 || out_h > 65535) return fail(B2_ERR_INVALID, "resize: more than 65535 rows");
+    return B2_OK;
+}
+int b2_resize_image(int device, int kind, const void* in, int in_w, int in_h, size_t in_pitch, void* out, int out_w, int out_h, size_t out_pitch) {
+    if (int rc = resizeCheck(kind, in, in_w, in_h, in_pitch, out_w, out_h)) return rc;
+    const size_t texel = (kind == B2_RESIZE_DEPTH || kind == B2_RESIZE_GENERIC_L16) ? 2 : 4;
+    if (!out || out_pitch < (size_t)out_w * texel) return fail(B2_ERR_INVALID, "resize: bad output image");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(B2_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)"); }
+    if (device < 0 || device >= ndev) return fail(B2_ERR_INVALID, "bad device index");
+    CU(cudaSetDevice(device));
+    uint8_t* dOut = nullptr;
+    const size_t dPitch = alignUp((size_t)out_w * texel, 128);
+    CU(cudaMalloc((void**)&dOut, dPitch * out_h));
+    int rc = resize_host_to_device(kind, in, in_w, in_h, in_pitch, dOut, dPitch, out_w, out_h, cudaStreamPerThread);
+    cudaError_t e = rc ? cudaSuccess : cudaMemcpy2DAsync(out, out_pitch, dOut, dPitch, (size_t)out_w * texel, (size_t)out_h, cudaMemcpyDeviceToHost, cudaStreamPerThread);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
+    cudaFree(dOut);
+    if (rc) return fail(B2_ERR_CUDA, cudaGetErrorString((cudaError_t)rc));
+    CU(e);
+    return B2_OK;
+}
+int b2layer_resize_plane(b2layer* l, int plane, int kind, const void* in, int in_w, int in_h, size_t in_pitch) {
+    if (!l || plane < 0 || plane > 2) return fail(B2_ERR_INVALID, "b2layer_resize_plane: bad arguments");
+    if (int rc = resizeCheck(kind, in, in_w, in_h, in_pitch, l->w, l->h)) return rc;
+    const bool l16 = kind == B2_RESIZE_DEPTH || kind == B2_RESIZE_GENERIC_L16;
+    if (l16 != (plane == 1)) return fail(B2_ERR_INVALID, "b2layer_resize_plane: the depth plane takes the L16 kinds, the others the RGBA kinds");
+    CU(cudaSetDevice(l->device));
+    const DevLevel& L = l->plane[plane];
+    if (int rc = resize_host_to_device(kind, in, in_w, in_h, in_pitch, L.base, (size_t)L.pitch, l->w, l->h, cudaStreamPerThread))
+        return fail(B2_ERR_CUDA, cudaGetErrorString((cudaError_t)rc));
     return B2_OK;
 }
 }  // extern "C"

@@ -302,6 +302,25 @@ int b2layer_upload(b2layer*, int plane, const void* host, size_t host_pitch, con
  * blendColor color.d:453-526, bit-exact incl. the 32-bit wrap of the L16 products). */
 int b2pbr_draw_layer(b2pbr*, b2layer*, int x, int y, const b2_box2i* dirty_rects, int n, int mode);
 
+/* SURVEY §8(f) row 2, second half — ImageResizer (graphics/dplug/graphics/resizer.d): the resampling that fills a
+ * background widget's cache from its full-size images (PBRBackgroundGUI.resizeFun, pbrbackgroundgui.d:172-199).
+ * Semantics = resizer.d over the IN-TREE stb_image_resize port (graphics/dplug/graphics/stb_image_resize.d, i.e. the
+ * `DPLUG_USE_STB_IMAGE_RESIZE_V2 = false` branches), bit-exact; the default build's un-vendored stb_image_resize2 rounds
+ * differently.  kind selects pixel type and filter:
+ *   B2_RESIZE_DIFFUSE      resizeImageDiffuse       RGBA8, Magic Kernel Sharp 2013 at 86 %   (resizer.d:346-372)
+ *   B2_RESIZE_MATERIAL     resizeImageMaterial = resizeImageGeneric(RGBA): Catmull-Rom up / Mitchell down (resizer.d:39-64,374-376)
+ *   B2_RESIZE_DEPTH        resizeImageDepth(L16)    Magic Kernel Sharp 2021                  (resizer.d:171-197)
+ *   B2_RESIZE_GENERIC_L16  resizeImageGeneric(L16)  default filters                          (resizer.d:144-169)
+ *   B2_RESIZE_SMOOTHER     resizeImageSmoother      RGBA8, cubic B-spline                    (resizer.d:92-117)
+ * Equal sizes copy (sameSizeResize, resizer.d:453-465).  Both calls synchronise.
+ *  b2_resize_image: host image -> host image through the device `device`.
+ *  b2layer_resize_plane: host image -> plane 0 (diffuse), 1 (depth) or 2 (material) of a device-resident layer at the
+ *      layer's size — the widget cache never exists on the host. */
+enum { B2_RESIZE_DIFFUSE = 0, B2_RESIZE_MATERIAL = 1, B2_RESIZE_DEPTH = 2, B2_RESIZE_GENERIC_L16 = 3, B2_RESIZE_SMOOTHER = 4 };
+int b2_resize_image(int device, int kind, const void* in, int in_w, int in_h, size_t in_pitch, void* out, int out_w, int out_h,
+                    size_t out_pitch);
+int b2layer_resize_plane(b2layer*, int plane, int kind, const void* in, int in_w, int in_h, size_t in_pitch);
+
 /* SURVEY §8(f) row 1 — the post-composite per-pixel chain of GUIGraphics.doDraw, stages E-H (graphics.d:825-868),
  * fused into one pass over the composited twin: blit composited -> rendered, UIColorCorrection transfer tables
  * (pbrwidgets/dplug/pbrwidgets/colorcorrection.d:128-170), reorderComponents(pf) with alpha = 255

@@ -71,6 +71,11 @@ int b2ref_present(b2ref_imageref composited, b2ref_imageref rendered, int pixel_
 size_t b2ref_screenshot_qb(b2ref_imageref rendered, int pixel_format, b2ref_imageref depth, uint8_t* out, size_t cap);
 int b2ref_screenshot_png_pixels(b2ref_imageref rendered, int pixel_format, uint8_t* out_rgba, size_t out_pitch);
 
+/* ---- ImageResizer over the in-tree stb_image_resize port (graphics/dplug/graphics/resizer.d, stb_image_resize.d; the
+ * `DPLUG_USE_STB_IMAGE_RESIZE_V2 = false` branches).  kind: 0 diffuse, 1 material / generic RGBA, 2 depth, 3 generic L16,
+ * 4 smoother RGBA */
+int b2ref_resize_image(int kind, const void* in, int in_w, int in_h, size_t in_pitch, void* out, int out_w, int out_h, size_t out_pitch);
+
 /* ---- widget cache -> level-0 maps: blit (pbrbackgroundgui.d:147-162) or blendWithAlpha (bufferedelement.d:118-131) */
 int b2ref_draw_layer(b2ref_imageref dstD, b2ref_imageref dstZ, b2ref_imageref dstM, b2ref_imageref srcD, b2ref_imageref srcZ,
                      b2ref_imageref srcM, b2ref_imageref opD, b2ref_imageref opZ, b2ref_imageref opM, int x, int y,

@@ -71,6 +71,7 @@ def lib():
             "b2ref_draw_layer": (I, [imageref] * 9 + [I, I, C.POINTER(box2i), I, I]),
             "b2ref_screenshot_qb": (C.c_size_t, [imageref, I, imageref, V, C.c_size_t]),
             "b2ref_screenshot_png_pixels": (I, [imageref, I, V, C.c_size_t]),
+            "b2ref_resize_image": (I, [I, V, I, I, C.c_size_t, V, I, I, C.c_size_t]),
             "b2ref_present": (I, [imageref, imageref, I, imageref, I, I, C.POINTER(box2i), I, V, I]),
             "b2ref_tile_areas": (I, [C.POINTER(box2i), I, I, I, C.POINTER(box2i), I]),
             "b2ref_remove_overlapping_areas": (I, [C.POINTER(box2i), I, C.POINTER(box2i), I]),
@@ -227,6 +228,20 @@ def screenshotPixels(rendered, pixelFormat):
     out = np.empty_like(rendered)
     assert lib().b2ref_screenshot_png_pixels(imageref(rendered.shape[1], rendered.shape[0], rendered.strides[0], rendered.ctypes.data), pixelFormat,
                                              out.ctypes.data_as(C.c_void_p), out.strides[0]) == 0
+    return out
+
+
+RESIZE_DIFFUSE, RESIZE_MATERIAL, RESIZE_DEPTH, RESIZE_GENERIC_L16, RESIZE_SMOOTHER = range(5)
+
+
+def resizeImage(kind, src, out_w, out_h):
+    """ImageResizer over the in-tree stb_image_resize port (resizer.d / stb_image_resize.d, V2 = false): src is (h, w, 4)
+    uint8 for the RGBA kinds, (h, w) uint16 for the L16 kinds"""
+    src = np.ascontiguousarray(src)
+    out = np.zeros((out_h, out_w) + src.shape[2:], dtype=src.dtype)
+    rc = lib().b2ref_resize_image(kind, src.ctypes.data_as(C.c_void_p), src.shape[1], src.shape[0], src.strides[0],
+                                  out.ctypes.data_as(C.c_void_p), out_w, out_h, out.strides[0])
+    assert rc == 0
     return out
 
 
