@@ -11,7 +11,7 @@
 // host derives from the port's contributor / coefficient arithmetic (set-up work, a few thousand floats):
 //   k_resize_h: decode (v / 255, v / 65535: IEEE division) + horizontal sums, one thread per (output column, input row);
 //   k_resize_v: vertical sums + encode (saturate, * max, + 0.5, truncate), one thread per output pixel.
-// Bit-exact against the restated port (oracle/ref_resizer.cpp, which keeps the ring buffer and the scatter).  The
+// Bit-exact against a CPU restatement of the port that keeps its ring buffer and scatter (tests/test_resizer.py).  The
 // default build of the reference calls the un-vendored stb_image_resize2 package instead: same kernels, different float
 // operation order — parity with that build is unpinned.
 #include <cmath>
