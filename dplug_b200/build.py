@@ -23,7 +23,7 @@ UNITS = [
     ("mip_fused.cu", ["-fmad=false"] + (["-DB2_MIP_DEBUG"] if os.environ.get("B2_MIP_DEBUG") else [])),
     ("pbr_exact.cu", ["-fmad=false"]),
     ("resizer.cu", ["-fmad=false"]),
-    ("pbr_tex.cu", ["-DB2_TEX_MIN_CTAS=%s" % os.environ.get("B2_TEX_MIN_CTAS", "5")]),
+    ("pbr_tex.cu", ["-DB2_TEX_MIN_CTAS=%s" % os.environ.get("B2_TEX_MIN_CTAS", "5")] + ["-D%s=%s" % (k, os.environ[k]) for k in ("B2_PAIR_MIN_CTAS",) if k in os.environ]),
 ]
 
 

@@ -36,7 +36,7 @@ void launch_screenshot_qb(uint32_t* vox, const DevLevel& src, const DevLevel& de
 void launch_fill32(const DevLevel& win, uint32_t value, cudaStream_t s);
 void launch_pbr_exact(const PbrArgs& args, int gridBlocks, cudaStream_t stream);
 constexpr int kQuadrantRows = 32;   // rows of a full-height warp quadrant of k_pbr_tex (CTA box = 64 x 64)
-void launch_pbr_tex(const PbrArgs& args, bool skyGather, cudaStream_t stream);
+void launch_pbr_tex(const PbrArgs& args, bool skyGather, int kernel, cudaStream_t stream);
 void sky_atlas_layout(const DevLevel* levels, int n, int* ox, int* oy, int* aw, int* ah);
 void launch_sky_atlas(const DevLevel* levels, int n, const int* ox, const int* oy, int aw, int ah, uint32_t* out, cudaStream_t s);
 void launch_sample(const DevLevel* levels, int nLevels, int color, int kind, int n, const float* lvl, const float* x,
@@ -1165,12 +1165,17 @@ static int pbrComposite(b2pbr* c, const b2_box2i* areas, int n, b2mip* diffuse, 
             A.skyMaxY[l] = (float)(c->sky->levels[l].h - 1);
             A.skyOx[l] = (float)c->skyOx[l];
             A.skyOy[l] = (float)c->skyOy[l];
+            const float sc = ldexpf(1.0f, -l);
+            A.skyCX[l] = make_float4(A.skyOx[l], A.skyOx[l] + 0.5f, A.skyOx[l] + A.skyMaxX[l] + 0.5f, sc);
+            A.skyCY[l] = make_float4(A.skyOy[l], A.skyOy[l] + 0.5f, A.skyOy[l] + A.skyMaxY[l] + 0.5f, sc);
         }
     }
     for (int l = 0; l < A.nDiffuse; ++l) A.texD[l] = diffuse->tex[l];
     for (int l = 0; l < A.nDepth; ++l) A.texZ[l] = depth->tex[l];
     traceBegin(c, "PBR compositeTile");
-    if (fast) launch_pbr_tex(A, c->mode == B2_MODE_FAST_SKY_GATHER, c->stream);
+    static const int pairKernel = getenv("B2_PBR_PAIR") ? atoi(getenv("B2_PBR_PAIR")) : 1;   // tuning aid: 0 = one row per lane (k_pbr_tex)
+    A.negZero2 = 0x8000000080000000ull;
+    if (fast) launch_pbr_tex(A, c->mode == B2_MODE_FAST_SKY_GATHER, pairKernel ? 0 : 1, c->stream);
     else launch_pbr_exact(A, A.nBoxes, c->stream);
     c->launches++;
     traceEnd(c);

@@ -79,6 +79,11 @@ struct PbrArgs {
     cudaTextureObject_t texSkyLin;   // the same array with the linear filter (B2_SKY_HW experiment)
     float skyMaxX[kMaxSkyLevels], skyMaxY[kMaxSkyLevels];   // w - 1, h - 1 of every skybox level
     float skyOx[kMaxSkyLevels], skyOy[kMaxSkyLevels];       // atlas position of texel (0, 0) of every level
+    // the filtered skybox fetch of level l samples the atlas at clamp(fma(sky, 2^-l, o), lo, hi) per axis, with
+    // lo = o + 0.5 and hi = o + (size - 1) + 0.5 (texel centres: the reference's edge rules): {o, lo, hi, 2^-l}, one
+    // 128-bit constant load per level and axis
+    float4 skyCX[kMaxSkyLevels], skyCY[kMaxSkyLevels];
+    unsigned long long negZero2;   // (-0.0f, -0.0f): the addend of exact packed products (mip_math.cuh, mulToAdd2)
 };
 
 }  // namespace b2
