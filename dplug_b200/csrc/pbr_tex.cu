@@ -587,7 +587,8 @@ struct alignas(16) CtaP {
 static_assert(sizeof(CtaP) <= sizeof(CtaT), "same shared-memory footprint as k_pbr_tex");
 
 #ifndef B2_PAIR_MIN_CTAS
-#define B2_PAIR_MIN_CTAS 4      // 128 registers, no spills.  Measured: 3 CTAs/SM (165 registers) 0.176 ms, 4: 0.157 ms, 5 (96 registers, 40 bytes spilled): 0.160 ms
+#define B2_PAIR_MIN_CTAS 4      // 128 registers, no spills.  Measured: 3 CTAs/SM (165 registers) 0.176 ms, 4: 0.157 ms, 5 (96 registers, 40 bytes spilled): 0.160 ms;
+                                // 5 CTAs with the level-5 column sums in shared memory (ptxas then spills 188 bytes): 0.170 ms; RSQRTSS table staged in shared memory: 0.161 ms
 #endif
 
 template <bool HAS_SKY, bool ALL_PASSES>

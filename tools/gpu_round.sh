@@ -9,5 +9,5 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_re
 B2_PIPE_DEBUG=1 python bench.py --steps 3 --warmup 1 --no-cpu-baseline --extras 0 2>&1 >/dev/null | grep "b2pbr pipe" | tail -6
 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --graph 0 --extras 0 > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches_frame.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --graph 0 --extras 0 > gpurun_out/ncu_l.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_pbr_tex -s 4 -c 1 -o gpurun_out/${T}_prof_pbr_tex -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --graph 0 --extras 0 > gpurun_out/ncu_f.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_pbr_pair -s 4 -c 1 -o gpurun_out/${T}_prof_pbr_pair -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --graph 0 --extras 0 > gpurun_out/ncu_f.log 2>&1
 ls -la gpurun_out | grep ${T}_
