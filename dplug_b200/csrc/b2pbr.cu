@@ -1013,7 +1013,7 @@ static int stripRowsFor(const b2_box2i* areas, int n) {
     // Wave model: a launch runs ceil(strips / resident warps) waves, each as long as one strip (R rows + a staging cost
     // worth ~6 rows).  Long lists take full-height strips (least staging per pixel); short ones — the 620 x 330 default
     // UI, the boundary tiles of a row band — are cut finer when that fills the last wave better.
-    const long long slots = 148ll * 20;            // 5 CTAs x 4 warps per SM
+    static const long long slots = 148ll * (getenv("B2_PBR_PAIR") && atoi(getenv("B2_PBR_PAIR")) == 0 ? 20 : 16);   // resident warps: k_pbr_pair 4 CTAs x 4 warps per SM (k_pbr_tex: 5 x 4)
     int best = full; long long bestCost = -1;
     for (int R = full; R >= 4; R >>= 1) {
         long long strips = 0;

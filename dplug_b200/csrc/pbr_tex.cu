@@ -608,21 +608,47 @@ __global__ void __launch_bounds__(T_WARPS * 32, B2_PAIR_MIN_CTAS) k_pbr_pair(con
         const int nRows = (cbox.maxy - cbox.miny) + T_HALO_UP + 1;          // row B = j + 1 <= last row: its stencil ends on the row below the box
         const int nQuads = (cbox.maxx + T_HALO_X - cx0 + 3) >> 2;
         const uint32_t magic = 0xffffffffu / (uint32_t)nQuads + 1u;
-        for (uint32_t idx = threadIdx.x; idx < (uint32_t)(nRows * nQuads); idx += T_WARPS * 32) {
-            const uint32_t r = __umulhi(idx, magic);
-            const int q = (int)(idx - r * (uint32_t)nQuads);
-            const int gy = max(0, min(ry0 + (int)r, H - 1)), gx = cx0 + 4 * q;
-            const uint16_t* src = rowPtr<uint16_t>(D0, gy);
-            float4 v;
-            if (gx >= 0 && gx + 3 < W) {
-                const uint2 t = __ldg(reinterpret_cast<const uint2*>(src + gx));
-                v = make_float4(tU16(t.x & 0xffffu), tU16(t.x >> 16), tU16(t.y & 0xffffu), tU16(t.y >> 16));
-            } else {
-                v = make_float4(tU16(__ldg(src + max(0, min(gx, W - 1)))), tU16(__ldg(src + max(0, min(gx + 1, W - 1)))),
-                                tU16(__ldg(src + max(0, min(gx + 2, W - 1)))), tU16(__ldg(src + max(0, min(gx + 3, W - 1)))));
-            }
+        const uint32_t total = (uint32_t)(nRows * nQuads);
+        auto put = [&](uint32_t r, int q, float4 v) {
             v = make_float4(__fmul_rn(v.x, multUshort), __fmul_rn(v.y, multUshort), __fmul_rn(v.z, multUshort), __fmul_rn(v.w, multUshort));
             *reinterpret_cast<float4*>(&S.depth[r][4 * q]) = v;
+        };
+        if (cx0 >= 0 && cx0 + 4 * nQuads <= W) {
+            // window inside the image horizontally (all but the boxes on the left / right edge): four 64-bit loads per thread
+            // in flight before the first conversion — the CTA starts with nothing else to hide their latency
+            for (uint32_t base = threadIdx.x; base < total; base += 4 * T_WARPS * 32) {
+                uint2 t[4];
+                uint32_t rr[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t idx = base + u * T_WARPS * 32;
+                    rr[u] = __umulhi(idx, magic);
+                    if (idx < total) {
+                        const int q = (int)(idx - rr[u] * (uint32_t)nQuads);
+                        t[u] = __ldg(reinterpret_cast<const uint2*>(rowPtr<uint16_t>(D0, max(0, min(ry0 + (int)rr[u], H - 1))) + cx0 + 4 * q));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t idx = base + u * T_WARPS * 32;
+                    if (idx < total)
+                        put(rr[u], (int)(idx - rr[u] * (uint32_t)nQuads), make_float4(tU16(t[u].x & 0xffffu), tU16(t[u].x >> 16), tU16(t[u].y & 0xffffu), tU16(t[u].y >> 16)));
+                }
+            }
+        } else {
+            for (uint32_t idx = threadIdx.x; idx < total; idx += T_WARPS * 32) {
+                const uint32_t r = __umulhi(idx, magic);
+                const int q = (int)(idx - r * (uint32_t)nQuads);
+                const int gy = max(0, min(ry0 + (int)r, H - 1)), gx = cx0 + 4 * q;
+                const uint16_t* src = rowPtr<uint16_t>(D0, gy);
+                if (gx >= 0 && gx + 3 < W) {
+                    const uint2 t = __ldg(reinterpret_cast<const uint2*>(src + gx));
+                    put(r, q, make_float4(tU16(t.x & 0xffffu), tU16(t.x >> 16), tU16(t.y & 0xffffu), tU16(t.y >> 16)));
+                } else {
+                    put(r, q, make_float4(tU16(__ldg(src + max(0, min(gx, W - 1)))), tU16(__ldg(src + max(0, min(gx + 1, W - 1)))),
+                                          tU16(__ldg(src + max(0, min(gx + 2, W - 1)))), tU16(__ldg(src + max(0, min(gx + 3, W - 1))))));
+                }
+            }
         }
     }
 

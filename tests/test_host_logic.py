@@ -91,12 +91,13 @@ def test_exact_mip_kernels_contain_no_fused_multiply_add(b2):
 def test_blackwell_native_paths_in_sass(b2):
     """SASS evidence of the hardware paths DESIGN.md claims: the large cubic levels are fed by the TMA engine (1-D bulk
     asynchronous copies completing on mbarriers: UBLKCP + SYNCS), and the lighting kernel's mip / skybox samplers run on
-    the texture units (TEX for the bilinear fetches, TLD4 for the gather variant)."""
+    the texture units (TEX for the bilinear fetches, TLD4 for the gather variant); the default lighting kernel computes two
+    rows per lane with packed FP32 instructions (FFMA2 / FADD2 / FMUL2)."""
     import shutil
     import subprocess
     if not shutil.which("cuobjdump"):
         pytest.skip("cuobjdump not on PATH")
-    want = {"mip_kernels.o": ("UBLKCP", "SYNCS"), "pbr_tex.o": ("TEX", "TLD4")}
+    want = {"mip_kernels.o": ("UBLKCP", "SYNCS"), "pbr_tex.o": ("TEX", "TLD4", "FFMA2", "FADD2", "FMUL2")}
     for obj, mnemonics in want.items():
         path = os.path.join(ROOT, "dplug_b200", "build", obj)
         if not os.path.exists(path):
