@@ -21,6 +21,7 @@ import dplug.math.box;
 import dplug.math.vector;
 import dplug.graphics;
 import dplug.gui.compositor;
+import dplug.window.window : WindowPixelFormat;
 
 nothrow @nogc:
 
@@ -50,6 +51,12 @@ extern(C) nothrow @nogc
                                   b2_imageref diffuseL0, b2_imageref materialL0, b2_imageref depthL0);
     int b2_host_register(void* ptr, size_t bytes);
     int b2_host_unregister(void* ptr);
+    // screenshot encoders (gui/dplug/gui/screencap.d) on the device-resident rendered buffer, ImageResizer on the device
+    size_t b2pbr_screenshot_qb_size(const(b2pbr)*);
+    int b2pbr_screenshot_qb(b2pbr*, int pixelFormat, void* out_, size_t cap);
+    size_t b2pbr_screenshot_png_size(const(b2pbr)*);
+    int b2pbr_screenshot_png(b2pbr*, int pixelFormat, void* out_, size_t cap, size_t* written);
+    int b2_resize_image(int device, int kind, const(void)* in_, int inW, int inH, size_t inPitch, void* out_, int outW, int outH, size_t outPitch);
     int b2pbr_profile_enable(b2pbr*, int on);
     int b2pbr_trace_json(b2pbr*, char* buf, size_t cap, size_t* needed);
 
@@ -134,6 +141,35 @@ nothrow:
         size_t needed;
         b2pbr_trace_json(_h, buf.ptr, buf.length, &needed);
         return needed;
+    }
+
+    /// encodeScreenshotAsQB / encodeScreenshotAsPNG (gui/dplug/gui/screencap.d:21-136) for an `onScreenshot` override
+    /// (graphics.d:140-147): built on the device from the rendered frame and the depth map; free with `free(slice.ptr)`.
+    /// WindowPixelFormat (window/dplug/window/window.d:155-160: BGRA8, ARGB8, RGBA8) -> B2_PF_* (RGBA8 = 0, BGRA8 = 1, ARGB8 = 2)
+    static int toB2PixelFormat(WindowPixelFormat pf)
+    {
+        final switch (pf)
+        {
+            case WindowPixelFormat.RGBA8: return 0;
+            case WindowPixelFormat.BGRA8: return 1;
+            case WindowPixelFormat.ARGB8: return 2;
+        }
+    }
+    ubyte[] encodeScreenshotAsQB(WindowPixelFormat pf)
+    {
+        import core.stdc.stdlib : malloc;
+        size_t n = b2pbr_screenshot_qb_size(_h);
+        ubyte* p = cast(ubyte*) malloc(n);
+        if (p is null || b2pbr_screenshot_qb(_h, toB2PixelFormat(pf), p, n) != 0) return null;
+        return p[0 .. n];
+    }
+    ubyte[] encodeScreenshotAsPNG(WindowPixelFormat pf)
+    {
+        import core.stdc.stdlib : malloc;
+        size_t n = b2pbr_screenshot_png_size(_h), written;
+        ubyte* p = cast(ubyte*) malloc(n);
+        if (p is null || b2pbr_screenshot_png(_h, toB2PixelFormat(pf), p, n, &written) != 0) return null;
+        return p[0 .. written];
     }
 
     // <LEGACY> setters, legacypbr.d:75-123

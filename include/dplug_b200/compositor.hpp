@@ -143,11 +143,43 @@ public:
     void setSkybox(ImageRef<const RGBA> image) { check(b2pbr_set_skybox(_h, (const uint8_t*)image.pixels, image.w, image.h, image.pitch)); }
     b2pbr* handle() const { return _h; }
 
+    // screenshot encoders, gui/dplug/gui/screencap.d:21-136, on the rendered buffer of doDraw stage G.bis (graphics.d:848-857)
+    std::vector<unsigned char> encodeScreenshotAsQB(int pixelFormat) {
+        std::vector<unsigned char> out(b2pbr_screenshot_qb_size(_h));
+        check(b2pbr_screenshot_qb(_h, pixelFormat, out.data(), out.size()));
+        return out;
+    }
+    std::vector<unsigned char> encodeScreenshotAsPNG(int pixelFormat) {
+        std::vector<unsigned char> out(b2pbr_screenshot_png_size(_h));
+        size_t written = 0;
+        check(b2pbr_screenshot_png(_h, pixelFormat, out.data(), out.size(), &written));
+        out.resize(written);
+        return out;
+    }
+
 private:
     b2pbr* _h = nullptr;
     b2pbr_params _p;
     void push() { check(b2pbr_set_params(_h, &_p)); }
     void set3(float* dst, float a, float b, float c) { dst[0] = a; dst[1] = b; dst[2] = c; push(); }
+};
+
+// ImageResizer, graphics/dplug/graphics/resizer.d (in-tree stb_image_resize port semantics): resampling on the device
+class ImageResizer {
+public:
+    explicit ImageResizer(int device = 0) : _device(device) {}
+    void resizeImageDiffuse(ImageRef<const RGBA> in, ImageRef<RGBA> out) { run(B2_RESIZE_DIFFUSE, in.pixels, in.w, in.h, in.pitch, out.pixels, out.w, out.h, out.pitch); }
+    void resizeImageMaterial(ImageRef<const RGBA> in, ImageRef<RGBA> out) { run(B2_RESIZE_MATERIAL, in.pixels, in.w, in.h, in.pitch, out.pixels, out.w, out.h, out.pitch); }
+    void resizeImageGeneric(ImageRef<const RGBA> in, ImageRef<RGBA> out) { resizeImageMaterial(in, out); }
+    void resizeImageSmoother(ImageRef<const RGBA> in, ImageRef<RGBA> out) { run(B2_RESIZE_SMOOTHER, in.pixels, in.w, in.h, in.pitch, out.pixels, out.w, out.h, out.pitch); }
+    void resizeImageDepth(ImageRef<const L16> in, ImageRef<L16> out) { run(B2_RESIZE_DEPTH, in.pixels, in.w, in.h, in.pitch, out.pixels, out.w, out.h, out.pitch); }
+    void resizeImageGeneric(ImageRef<const L16> in, ImageRef<L16> out) { run(B2_RESIZE_GENERIC_L16, in.pixels, in.w, in.h, in.pitch, out.pixels, out.w, out.h, out.pitch); }
+
+private:
+    int _device;
+    void run(int kind, const void* in, int iw, int ih, size_t ip, void* out, int ow, int oh, size_t op) {
+        check(b2_resize_image(_device, kind, in, iw, ih, ip, out, ow, oh, op));
+    }
 };
 
 }  // namespace b2
