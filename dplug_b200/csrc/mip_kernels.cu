@@ -31,14 +31,17 @@ __global__ void __launch_bounds__(256) k_cubic_rgba4(DevLevel dst, DevLevel src,
 // (cp.async.bulk.shared.global, the TMA engine: SASS UBLKCP) that complete on mbarriers; four consumer warps read a
 // stage when its barrier has flipped and hand it back through a second barrier.  No load instruction, no address
 // arithmetic and no scoreboard wait for global memory is left in the consumers' instruction stream, and TMA_STAGES row
-// pairs (33 KB) per CTA are in flight instead of what one round of register loads can hold.  The vertical [1 3 3 1] is
-// carried as one partial sum per column: with A..D = rows 2y-1 .. 2y+2 split into even / odd byte lanes,
-// V(y) = (A + 3B) + 3C + D and the carry for y + 1 is C + 3D, so every source row is read once.
-// Measured on the 8192^2 pyramid (4096^2 -> 2048^2, 84 MB): 18 us against 21.2 us for k_cubic_rgba4; a register-only
-// walking variant (loads by the consumers themselves, one row pair ahead) reached the same 18 us — at ~45 integer
-// instructions per destination texel (two 16-bit lanes per 32-bit operation) the level is bound by the ALU pipe, not by
-// HBM (13 us) — and a deeper register prefetch (163 registers) fell to 25.7 us.
-constexpr int TMA_STRIP = 256;                        // destination columns per CTA (128 consumer threads x 2 texels)
+// pairs per CTA are in flight instead of what one round of register loads can hold.
+//
+// Arithmetic per consumer thread = FOUR destination texels, horizontal filter first.  The [1 3 3 1] x [1 3 3 1] sum is
+// separable and integer, so the order is free: every source row is filtered horizontally once (H = (a + d) + 3 (b + c)
+// on the two 16-bit lane pairs of the RGBA texels: ten source texels give four H values), and the vertical
+// [1 3 3 1] is carried as ONE partial sum per destination texel: with A..D = H of rows 2y-1 .. 2y+2,
+// V(y) = (A + 3B) + 3C + D and the carry for y + 1 is C + 3D.  ~35 integer instructions per destination texel (the first
+// version — two texels per thread, vertical sums per source column, then the horizontal filter — needed ~45 and was
+// bound by the ALU pipe: 18 us for the 4096^2 -> 2048^2 level of the 8192^2 pyramid against 13 us of HBM time).
+constexpr int TMA_TEXELS = 4;                         // destination texels per consumer thread
+constexpr int TMA_STRIP = 128 * TMA_TEXELS;           // destination columns per CTA (128 consumer threads)
 #ifndef B2_TMA_ROWS
 #define B2_TMA_ROWS 16
 #endif
@@ -47,8 +50,8 @@ constexpr int TMA_STRIP = 256;                        // destination columns per
 #endif
 constexpr int TMA_ROWS = B2_TMA_ROWS;                 // destination rows a CTA walks
 constexpr int TMA_STAGES = B2_TMA_STAGES;             // ring depth, in source-row pairs
-constexpr int TMA_ROW_TEXELS = 2 * TMA_STRIP + 8;     // source texels per staged row: columns [c0, c0 + 520), c0 = 2*x0 - 4
-constexpr int TMA_ROW_BYTES = TMA_ROW_TEXELS * 4;     // 2080, a multiple of 16
+constexpr int TMA_ROW_TEXELS = 2 * TMA_STRIP + 8;     // source texels per staged row: columns [c0, c0 + 2 * TMA_STRIP + 8), c0 = 2*x0 - 4
+constexpr int TMA_ROW_BYTES = TMA_ROW_TEXELS * 4;     // a multiple of 16
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(uint64_t* bar, int count) {
@@ -106,63 +109,62 @@ __global__ void __launch_bounds__(160) k_cubic_rgba_tma(DevLevel dst, DevLevel s
         return;
     }
 
-    // ---------------- consumers: thread = two destination texels x, x + 1 (source columns 2x-1 .. 2x+4)
+    // ---------------- consumers: thread = four destination texels x .. x + 3 (source columns 2x-1 .. 2x+8)
     const int t = threadIdx.x;                                        // 0 .. 127
-    const int x = x0 + 2 * t;
-    const bool active = x < r.maxx && 2 * x < sw && x + 1 >= r.minx;
-    // staged-row indices of the six source columns (clamped to the image: mipmap.d:915-935)
-    int ci[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) ci[k] = max(0, min(2 * x - 1 + k, sw - 1)) - c0;
-    const bool vec = active && 2 * x + 3 <= sw - 1;                   // columns 2x .. 2x+3 as one 128-bit shared load
-    auto readRow = [&](const uint32_t* row, uint32_t (&e)[6], uint32_t (&o)[6]) {
-        uint32_t v[6];
+    const int x = x0 + TMA_TEXELS * t;
+    const bool active = x < r.maxx && 2 * x < sw && x + TMA_TEXELS - 1 >= r.minx;
+    const bool vec = active && 2 * x + 7 <= sw - 1;                   // columns 2x .. 2x+7 as two 128-bit shared loads
+    const int cL = max(0, min(2 * x - 1, sw - 1)) - c0, cR = max(0, min(2 * x + 8, sw - 1)) - c0;   // outer columns, clamped to the image (mipmap.d:915-935)
+    const int cM = 2 * x - c0;
+    // horizontal [1 3 3 1] of one staged source row: he / ho[u] = even / odd byte lanes of destination texel x + u
+    auto hrow = [&](const uint32_t* row, uint32_t (&he)[TMA_TEXELS], uint32_t (&ho)[TMA_TEXELS]) {
+        uint32_t v[2 * TMA_TEXELS + 2];
         if (vec) {
-            const uint4 q = *reinterpret_cast<const uint4*>(row + ci[1]);
-            v[0] = row[ci[0]]; v[1] = q.x; v[2] = q.y; v[3] = q.z; v[4] = q.w; v[5] = row[ci[5]];
+            const uint4 q0 = *reinterpret_cast<const uint4*>(row + cM), q1 = *reinterpret_cast<const uint4*>(row + cM + 4);
+            v[0] = row[cL]; v[1] = q0.x; v[2] = q0.y; v[3] = q0.z; v[4] = q0.w; v[5] = q1.x; v[6] = q1.y; v[7] = q1.z; v[8] = q1.w; v[9] = row[cR];
         } else {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) v[k] = row[ci[k]];
+            for (int k = 0; k < 2 * TMA_TEXELS + 2; ++k) v[k] = row[max(0, min(2 * x - 1 + k, sw - 1)) - c0];
         }
+        uint32_t e[2 * TMA_TEXELS + 2], o[2 * TMA_TEXELS + 2];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { e[k] = evenBytes(v[k]); o[k] = oddBytes(v[k]); }
+        for (int k = 0; k < 2 * TMA_TEXELS + 2; ++k) { e[k] = evenBytes(v[k]); o[k] = oddBytes(v[k]); }
+#pragma unroll
+        for (int u = 0; u < TMA_TEXELS; ++u) {                        // columns 2(x+u)-1 .. 2(x+u)+2 = indices 2u .. 2u+3; <= 8 * 255 per lane
+            he[u] = (e[2 * u] + e[2 * u + 3]) + 3u * (e[2 * u + 1] + e[2 * u + 2]);
+            ho[u] = (o[2 * u] + o[2 * u + 3]) + 3u * (o[2 * u + 1] + o[2 * u + 2]);
+        }
     };
-    uint32_t pe[6], po[6];
+    uint32_t pe[TMA_TEXELS], po[TMA_TEXELS];                         // carried vertical partial sums
     for (int k = 0; k < nPairs; ++k) {
         const int st = k % TMA_STAGES;
         mbarWait(&full[st], (k / TMA_STAGES) & 1);
-        uint32_t ce[6], co[6], de[6], dO[6];
-        if (active) { readRow(ring[st][0], ce, co); readRow(ring[st][1], de, dO); }
+        uint32_t ce[TMA_TEXELS], co[TMA_TEXELS], de[TMA_TEXELS], dO[TMA_TEXELS];
+        if (active) { hrow(ring[st][0], ce, co); hrow(ring[st][1], de, dO); }
         __syncwarp();
         if (lane == 0) mbarArrive(&empty[st]);                        // this warp is done with the stage
         if (!active) continue;
         if (k == 0) {
 #pragma unroll
-            for (int c = 0; c < 6; ++c) { pe[c] = ce[c] + 3u * de[c]; po[c] = co[c] + 3u * dO[c]; }
+            for (int u = 0; u < TMA_TEXELS; ++u) { pe[u] = ce[u] + 3u * de[u]; po[u] = co[u] + 3u * dO[u]; }
             continue;
         }
         const int y = yb + k - 1;
-        uint32_t ve[6], vo[6];
+        uint32_t out[TMA_TEXELS];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            ve[c] = pe[c] + 3u * ce[c] + de[c];                       // <= 8 * 255 per 16-bit lane
-            vo[c] = po[c] + 3u * co[c] + dO[c];
-            pe[c] = ce[c] + 3u * de[c];
-            po[c] = co[c] + 3u * dO[c];
-        }
-        uint32_t o[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            // destination x+u: columns 2(x+u)-1 .. 2(x+u)+2 = indices 2u .. 2u+3 (already clamped through ci[])
-            const uint32_t sl = (ve[2 * u] + ve[2 * u + 3]) + 3u * (ve[2 * u + 1] + ve[2 * u + 2]) + 0x00200020u;
-            const uint32_t sh2 = (vo[2 * u] + vo[2 * u + 3]) + 3u * (vo[2 * u + 1] + vo[2 * u + 2]) + 0x00200020u;
-            o[u] = ((sl >> 6) & 0x00ff00ffu) | (((sh2 >> 6) & 0x00ff00ffu) << 8);
+        for (int u = 0; u < TMA_TEXELS; ++u) {
+            const uint32_t sl = (pe[u] + 3u * ce[u]) + (de[u] + 0x00200020u);          // <= 64 * 255 + 32 per 16-bit lane
+            const uint32_t sh2 = (po[u] + 3u * co[u]) + (dO[u] + 0x00200020u);
+            pe[u] = ce[u] + 3u * de[u];
+            po[u] = co[u] + 3u * dO[u];
+            out[u] = ((sl >> 6) & 0x00ff00ffu) | ((sh2 << 2) & 0xff00ff00u);
         }
         uint32_t* dp = rowPtrW<uint32_t>(dst, y);
-        if (x >= r.minx && x + 1 < r.maxx) *reinterpret_cast<uint2*>(dp + x) = make_uint2(o[0], o[1]);
+        if (x >= r.minx && x + TMA_TEXELS - 1 < r.maxx) *reinterpret_cast<uint4*>(dp + x) = make_uint4(out[0], out[1], out[2], out[3]);
         else {
-            if (x >= r.minx && x < r.maxx) dp[x] = o[0];
-            if (x + 1 >= r.minx && x + 1 < r.maxx) dp[x + 1] = o[1];
+#pragma unroll
+            for (int u = 0; u < TMA_TEXELS; ++u)
+                if (x + u >= r.minx && x + u < r.maxx) dp[x + u] = out[u];
         }
     }
 }
@@ -327,10 +329,12 @@ void launch_box_l16(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_
 }
 void launch_cubic_rgba(const DevLevel& dst, const DevLevel& src, Box r, cudaStream_t s) {
     static const int tmaOn = getenv("B2_CUBIC_TMA") ? atoi(getenv("B2_CUBIC_TMA")) : 1;      // tuning aid (0: never, 2: always — tests)
-    {   // large rectangles: the TMA-fed strip walker, when its CTAs fill the GPU
+    {   // large rectangles: the TMA-fed strip walker, when there are enough strips of 512 x 16 texels to fill the GPU
         const int x0 = (r.minx >> 2) << 2;
         const int strips = (r.maxx - x0 + TMA_STRIP - 1) / TMA_STRIP, chunks = (r.maxy - r.miny + TMA_ROWS - 1) / TMA_ROWS;
-        static const long long minCtas = getenv("B2_CUBIC_TMA_MIN") ? atoll(getenv("B2_CUBIC_TMA_MIN")) : 148 * 2;
+        // measured (us, TMA / four-texel register kernel): 4096^2 source 18.9 / 23.1; 8192 x 1024 (a band of the 16K canvas, 256 CTAs)
+        // 12.4 / 14.4; 2048^2 (128 CTAs) 8.6 / 8.4
+        static const long long minCtas = getenv("B2_CUBIC_TMA_MIN") ? atoll(getenv("B2_CUBIC_TMA_MIN")) : 256;
         if (tmaOn && ((long long)strips * chunks >= minCtas || tmaOn == 2) && r.maxx > r.minx && r.maxy > r.miny) {
             static bool attr = false;
             const size_t smem = sizeof(uint32_t) * TMA_STAGES * 2 * TMA_ROW_TEXELS;

@@ -202,3 +202,19 @@ def test_errors_are_reported(b2):
         z.generateNextLevel(2, (0, 0, 16, 16), 1)   # boxAlphaCovIntoPremul is RGBA-only (mipmap.d:594-595)
     e = b2.Mipmap(0, 4, 0, 0)   # zero-sized is supported (image.d:657-669)
     assert e.numLevels() == 0
+
+
+def test_cubic_tma_kernel_on_every_rectangle():
+    """The TMA-fed cubic kernel normally takes only rectangles that fill the GPU; B2_CUBIC_TMA=2 (read once per process)
+    forces it on every cubic RGBA step, so the small-size, odd-size and dirty-rectangle cases above run through its edge
+    handling (clamped outer columns, ragged strips, partial stores) in a child process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, B2_CUBIC_TMA="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-k", "not tma_kernel_on_every",
+                        "tests/test_gpu_mip.py::test_generate_next_level_full", "tests/test_gpu_mip.py::test_generate_next_level_dirty_rects",
+                        "tests/test_gpu_mip.py::test_cubic_wide_rectangles", "tests/test_gpu_mip.py::test_full_chain_diffuse_and_depth_recipes"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
