@@ -13,7 +13,7 @@ cs = []
 for k in range(3):                       # three bands' worth of maps so that the inputs do not stay in L2
     c = b2.PBRCompositor(0, band=(y0, y1)); c.resizeBuffers(W, H); c.set_stream(stream.cuda_stream)
     blk = (synth.diffuse(W, 512, synth.SEED + k), synth.material(W, 512, synth.SEED + k), synth.depth(W, 512, synth.SEED + k))
-    lo, hi = c.bandRows(0)[0], c.bandRows(0)[1]
+    lo, hi = y0, y1                      # own rows only (the halo rows come from the neighbours in a real frame)
     for yy in range(lo, hi, 512):
         n = min(512, hi - yy)
         c.diffuseMap.uploadRows(0, blk[0][:n], yy); c.materialMap.uploadRows(0, blk[1][:n], yy); c.depthMap.uploadRows(0, blk[2][:n], yy)
