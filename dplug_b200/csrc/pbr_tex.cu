@@ -583,8 +583,8 @@ static_assert(sizeof(WarpP) % 16 == 0, "per-warp shared block keeps 16-byte alig
 struct alignas(16) CtaP {
     float depth[T_ROWS][T_COLS];   // level-0 depth of the box + halo, times 1 / FACTOR_Z (the plane fit's exact operand)
     WarpP w[T_WARPS];
+    float4 skyC[2][kMaxSkyLevels]; // PbrArgs::skyCX / skyCY: the level varies per lane, and a constant load replays once per distinct index
 };
-static_assert(sizeof(CtaP) <= sizeof(CtaT), "same shared-memory footprint as k_pbr_tex");
 
 #ifndef B2_PAIR_MIN_CTAS
 #define B2_PAIR_MIN_CTAS 4      // 128 registers, no spills.  Measured: 3 CTAs/SM (165 registers) 0.176 ms, 4: 0.157 ms, 5 (96 registers, 40 bytes spilled): 0.160 ms;
@@ -650,6 +650,11 @@ __global__ void __launch_bounds__(T_WARPS * 32, B2_PAIR_MIN_CTAS) k_pbr_pair(con
                 }
             }
         }
+    }
+
+    if (HAS_SKY && threadIdx.x < 2 * kMaxSkyLevels) {
+        const int ax = threadIdx.x >= kMaxSkyLevels ? 1 : 0, l = threadIdx.x - ax * kMaxSkyLevels;
+        S.skyC[ax][l] = ax ? P.skyCY[l] : P.skyCX[l];
     }
 
     // ---------------------------------------------------------------- this warp's quadrant
@@ -875,7 +880,7 @@ __global__ void __launch_bounds__(T_WARPS * 32, B2_PAIR_MIN_CTAS) k_pbr_pair(con
             const int il0 = __float2int_rz(f2lo(lod)), il1 = __float2int_rz(f2hi(lod));   // linearMipmapSample, mipmap.d:149-160
             fl = lod - f2((float)il0, (float)il1);
             auto hw = [&](int level, float sx, float sy) {
-                const float4 kx = P.skyCX[level], ky = P.skyCY[level];     // {o, o + 0.5, o + size - 0.5, 2^-level}
+                const float4 kx = S.skyC[0][level], ky = S.skyC[1][level];   // {o, o + 0.5, o + size - 0.5, 2^-level}
                 const float cx = fminf(fmaxf(fmaf(sx, kx.w, kx.x), kx.y), kx.z);
                 const float cy = fminf(fmaxf(fmaf(sy, ky.w, ky.x), ky.y), ky.z);
                 return tex2D<float4>(P.texSkyLin, cx, cy);
@@ -1089,8 +1094,9 @@ static void dispatchTex(const PbrArgs& args, bool gather, size_t smem, bool setA
 }
 template <bool SKY, bool ALL>
 static void launchPairT(const PbrArgs& args, size_t smem, bool setAttr, cudaStream_t stream) {
-    if (setAttr) cudaFuncSetAttribute(k_pbr_pair<SKY, ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    else k_pbr_pair<SKY, ALL><<<args.nBoxes, T_WARPS * 32, smem, stream>>>(args);
+    (void)smem;
+    if (setAttr) cudaFuncSetAttribute(k_pbr_pair<SKY, ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaP));
+    else k_pbr_pair<SKY, ALL><<<args.nBoxes, T_WARPS * 32, sizeof(CtaP), stream>>>(args);
 }
 static void dispatchPair(const PbrArgs& args, size_t smem, bool setAttr, cudaStream_t stream) {
     const bool all = (args.passMask & 0xffu) == 0xffu, sky = args.nSky > 0;
