@@ -667,7 +667,7 @@ def run_default_single(args):
         "roofline": {"bound": "hbm", "kernel": "k_pbr_pair (fused lighting, 8 passes, two rows per lane on the packed FP32 pipe; mip and skybox samplers on the texture units)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": B, "launch_ms": r["light_ms"],
-                     "note": "the lighting pass is FP32-issue-bound (437 instructions per pixel against 16 B per pixel): "
+                     "note": "the lighting pass is FP32-issue-bound (433 instructions per pixel against 16 B per pixel): "
                              "the HBM fraction is the contract number, the issue utilisation is in profiles/"},
         "e2e": r["e2e"], "e2e_dirty_rect": r.get("e2e_dirty_rect"),
         "gpu_launches": r["launches"], "clocks": r.get("clocks"),
