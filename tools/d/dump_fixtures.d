@@ -10,7 +10,9 @@
 
     Runs the REAL dplug:gui PBRCompositor and dplug:graphics Mipmap (no restatement) on level-0 maps exported by
     tools/d/export_inputs.py and writes every mip level and the composited frame as raw little-endian files that
-    tools/d/import_outputs.py turns into tests/golden/*.npz with the keys tests/test_golden.py reads.  A maintainer with
+    tools/d/import_outputs.py turns into tests/golden/*.npz with the keys tests/test_golden.py reads.  It also dumps the
+    .qb screenshot of the frame and the three maps resized to 1/2 and 3/2 (SURVEY 8f rows 2 and 4), which the importer
+    compares with the CPU restatement.  A maintainer with
     LDC runs (adjust the dplug path in the dub recipe above):
 
         python tools/d/export_inputs.py /tmp/fx
@@ -36,6 +38,9 @@ import dplug.graphics.mipmap;
 import dplug.gui.boxlist;
 import dplug.gui.compositor;
 import dplug.gui.legacypbr;
+import dplug.gui.screencap;
+import dplug.graphics.resizer;
+import dplug.window.window : WindowPixelFormat;
 
 enum int PBR_TILE_MAX_WIDTH = 64;   // gui/dplug/gui/graphics.d:59-60
 enum int PBR_TILE_MAX_HEIGHT = 64;
@@ -136,6 +141,47 @@ void dumpCase(const(char)* root, const(char)* caseName)
         snprintf(name.ptr, name.length, "depth_l%d.raw", level);
         auto L = depthMap.levels[level];
         writeRaw(dir.ptr, name.ptr, L.scanlinePtr(0), L.w * 2, L.h, L.pitchInBytes());
+    }
+    // SURVEY 8(f) rows 2 and 4: the screenshot encoder and the resizer on the same data.
+    // encodeScreenshotAsQB (gui/dplug/gui/screencap.d:21-84) on the rendered buffer of an RGBA8 window: the composited
+    // frame with alpha = 255 (reorderComponents, graphics.d:1425-1452).
+    {
+        OwnedImage!RGBA rendered = mallocNew!(OwnedImage!RGBA)(W, H);
+        foreach (y; 0 .. H)
+        {
+            RGBA* src = composited.scanlinePtr(y);
+            RGBA* dst = rendered.scanlinePtr(y);
+            foreach (x; 0 .. W)
+                dst[x] = RGBA(src[x].r, src[x].g, src[x].b, 255);
+        }
+        ubyte[] qb = encodeScreenshotAsQB(rendered.toRef(), WindowPixelFormat.RGBA8, depthMap.levels[0].toRef());
+        writeRaw(dir.ptr, "screenshot.qb", qb.ptr, qb.length, 1, qb.length);
+        free(qb.ptr);
+        rendered.destroyFree();
+    }
+    // ImageResizer (graphics/dplug/graphics/resizer.d) as PBRBackgroundGUI.resizeFun calls it (pbrbackgroundgui.d:172-199):
+    // down to half size and up to 3/2.  NOTE: the result depends on DPLUG_USE_STB_IMAGE_RESIZE_V2 (stb_image_resize.d:157);
+    // the B200 path implements the `false` (in-tree port) branches — build dplug:graphics with that enum flipped to pin it.
+    {
+        ImageResizer resizer;
+        static immutable int[2][2] ratios = [[1, 2], [3, 2]];
+        foreach (k, ratio; ratios)
+        {
+            const int ow = W * ratio[0] / ratio[1], oh = H * ratio[0] / ratio[1];
+            OwnedImage!RGBA d2 = mallocNew!(OwnedImage!RGBA)(ow, oh), m2 = mallocNew!(OwnedImage!RGBA)(ow, oh);
+            OwnedImage!L16 z2 = mallocNew!(OwnedImage!L16)(ow, oh);
+            resizer.resizeImageDiffuse(diffuseMap.levels[0].toRef(), d2.toRef());
+            resizer.resizeImageMaterial(materialMap.levels[0].toRef(), m2.toRef());
+            resizer.resizeImageDepth(depthMap.levels[0].toRef().cropImageRef(box2i(0, 0, W, H)), z2.toRef());
+            char[64] name;
+            snprintf(name.ptr, name.length, "resized%d_diffuse.raw", cast(int) k);
+            writeRaw(dir.ptr, name.ptr, d2.scanlinePtr(0), ow * 4, oh, d2.pitchInBytes());
+            snprintf(name.ptr, name.length, "resized%d_material.raw", cast(int) k);
+            writeRaw(dir.ptr, name.ptr, m2.scanlinePtr(0), ow * 4, oh, m2.pitchInBytes());
+            snprintf(name.ptr, name.length, "resized%d_depth.raw", cast(int) k);
+            writeRaw(dir.ptr, name.ptr, z2.scanlinePtr(0), ow * 2, oh, z2.pitchInBytes());
+            d2.destroyFree(); m2.destroyFree(); z2.destroyFree();
+        }
     }
     printf("%s: %d x %d done\n", caseName, W, H);
 }
