@@ -172,7 +172,7 @@ void dumpCase(const(char)* root, const(char)* caseName)
             OwnedImage!L16 z2 = mallocNew!(OwnedImage!L16)(ow, oh);
             resizer.resizeImageDiffuse(diffuseMap.levels[0].toRef(), d2.toRef());
             resizer.resizeImageMaterial(materialMap.levels[0].toRef(), m2.toRef());
-            resizer.resizeImageDepth(depthMap.levels[0].toRef().cropImageRef(box2i(0, 0, W, H)), z2.toRef());
+            resizer.resizeImageDepth(depthMap.levels[0].toRef(), z2.toRef());
             char[64] name;
             snprintf(name.ptr, name.length, "resized%d_diffuse.raw", cast(int) k);
             writeRaw(dir.ptr, name.ptr, d2.scanlinePtr(0), ow * 4, oh, d2.pitchInBytes());
