@@ -116,6 +116,7 @@ SIGNATURES = {
     "b2layer_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(box2i), C.c_int]),
     "b2pbr_draw_layer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(box2i), C.c_int, C.c_int]),
     "b2_resize_image": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]),
+    "b2_resize_axis_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]),
     "b2layer_resize_plane": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t]),
     "b2pbr_screenshot_qb_size": (C.c_size_t, [C.c_void_p]),
     "b2pbr_screenshot_qb": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),

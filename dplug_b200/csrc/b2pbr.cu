@@ -31,6 +31,7 @@ void launch_copy_diffuse(const DevLevel& dst, const DevLevel& src, const Box* bo
 void launch_swizzle(const DevLevel& dst, const DevLevel& src, Box box, int pf, cudaStream_t s);
 void launch_layer(bool blend, const DevLevel* dst3, const DevLevel* src3, const DevLevel* op3, Box box, int px, int py, cudaStream_t s);
 void launch_present(const DevLevel& win, const DevLevel& src, Box box, int dx, int dy, int pf, const uint8_t* lut, cudaStream_t s);
+int resize_axis_table(int kind, int inSize, int outSize, int* start, int* src, float* coef, int cap);
 int resize_host_to_device(int kind, const void* in, int inW, int inH, size_t inPitch, uint8_t* dOut, size_t outPitch, int outW, int outH, cudaStream_t s);
 void launch_screenshot_qb(uint32_t* vox, const DevLevel& src, const DevLevel& depth, int W, int H, int pf, const uint8_t* lut, cudaStream_t s);
 void launch_fill32(const DevLevel& win, uint32_t value, cudaStream_t s);
@@ -779,6 +780,10 @@ static int resizeCheck(int kind, const void* in, int in_w, int in_h, size_t in_p
     if (in_pitch < (size_t)in_w * texel) return fail(B2_ERR_INVALID, "resize: input pitch smaller than a row");
     if (in_h > 65535 || out_h > 65535) return fail(B2_ERR_INVALID, "resize: more than 65535 rows");
     return B2_OK;
+}
+int b2_resize_axis_table(int kind, int in_size, int out_size, int* start, int* src, float* coef, int cap) {
+    if (kind < 0 || kind > 4 || in_size < 1 || out_size < 1 || cap < 0) return fail(B2_ERR_INVALID, "b2_resize_axis_table: bad arguments") * -1;
+    return resize_axis_table(kind, in_size, out_size, start, src, coef, cap);
 }
 int b2_resize_image(int device, int kind, const void* in, int in_w, int in_h, size_t in_pitch, void* out, int out_w, int out_h, size_t out_pitch) {
     if (int rc = resizeCheck(kind, in, in_w, in_h, in_pitch, out_w, out_h)) return rc;

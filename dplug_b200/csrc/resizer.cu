@@ -254,6 +254,20 @@ static cudaError_t resizeOnDevice(int kind, const uint8_t* dIn, size_t inPitch, 
     return e;
 }
 
+// host-only test hook: the gather table of one axis (b2_resize_axis_table)
+int resize_axis_table(int kind, int inSize, int outSize, int* start, int* src, float* coef, int cap) {
+    static const int filterOf[5] = {F_MKS_2013_86, F_DEFAULT, F_MKS_2021, F_DEFAULT, F_CUBICBSPLINE};
+    AxisTable T;
+    buildAxis(filterOf[kind], inSize, outSize, T);
+    const int n = (int)T.src.size();
+    if (start) memcpy(start, T.start.data(), sizeof(int) * (size_t)(outSize + 1));
+    for (int e = 0; e < n && e < cap; ++e) {
+        if (src) src[e] = T.src[e];
+        if (coef) coef[e] = T.coef[e];
+    }
+    return n;
+}
+
 // host image -> device image `dOut` (outPitch bytes per row) of outW x outH; synchronises
 int resize_host_to_device(int kind, const void* in, int inW, int inH, size_t inPitch, uint8_t* dOut, size_t outPitch, int outW, int outH, cudaStream_t s) {
     const bool l16 = kind == B2_RESIZE_DEPTH || kind == B2_RESIZE_GENERIC_L16;

@@ -320,6 +320,11 @@ enum { B2_RESIZE_DIFFUSE = 0, B2_RESIZE_MATERIAL = 1, B2_RESIZE_DEPTH = 2, B2_RE
 int b2_resize_image(int device, int kind, const void* in, int in_w, int in_h, size_t in_pitch, void* out, int out_w, int out_h,
                     size_t out_pitch);
 int b2layer_resize_plane(b2layer*, int plane, int kind, const void* in, int in_w, int in_h, size_t in_pitch);
+/* host only (no GPU needed; test hook): the gather table the two resampling kernels run for one axis of a resize of
+ * `kind` from in_size to out_size samples.  Output sample o is the sum, in this order and from 0,
+ * of source[clamp(src[e])] * coef[e] for e in [start[o], start[o + 1]).  Writes out_size + 1 values to `start` and up to
+ * `cap` entries to `src` / `coef` (any may be NULL); returns the number of entries (negative: -B2_ERR_*). */
+int b2_resize_axis_table(int kind, int in_size, int out_size, int* start, int* src, float* coef, int cap);
 
 /* SURVEY §8(f) row 1 — the post-composite per-pixel chain of GUIGraphics.doDraw, stages E-H (graphics.d:825-868),
  * fused into one pass over the composited twin: blit composited -> rendered, UIColorCorrection transfer tables

@@ -141,3 +141,47 @@ def test_background_cache_resized_on_the_device(b2, oracle):
     assert np.array_equal(c.diffuseMap.download(0), oracle.resizeImage(0, d, W, H))
     assert np.array_equal(c.materialMap.download(0), oracle.resizeImage(1, m, W, H))
     assert np.array_equal(c.depthMap.download(0), oracle.resizeImage(2, z, W, H))
+
+
+def _axis_table(kind, n_in, n_out):
+    import ctypes as C
+    from dplug_b200 import _lib
+    l = _lib.lib()
+    start = (C.c_int * (n_out + 1))()
+    n = l.b2_resize_axis_table(kind, n_in, n_out, start, None, None, 0)
+    assert n > 0
+    src, coef = (C.c_int * n)(), (C.c_float * n)()
+    assert l.b2_resize_axis_table(kind, n_in, n_out, start, src, coef, n) == n
+    return np.frombuffer(start, dtype=np.int32).copy(), np.frombuffer(src, dtype=np.int32).copy(), np.frombuffer(coef, dtype=np.float32).copy()
+
+
+def _gather(x, table, n_in, axis):
+    """out[o] = ((0 + x[clamp(src0)] * c0) + x[clamp(src1)] * c1) + ... in float32, one IEEE multiply and add per step:
+    what k_resize_h / k_resize_v do"""
+    start, src, coef = table
+    x = np.moveaxis(x, axis, 0)
+    out = np.zeros((len(start) - 1,) + x.shape[1:], dtype=np.float32)
+    for o in range(len(start) - 1):
+        acc = np.zeros(x.shape[1:], dtype=np.float32)
+        for e in range(start[o], start[o + 1]):
+            acc = (acc + (x[min(max(int(src[e]), 0), n_in - 1)] * np.float32(coef[e])).astype(np.float32)).astype(np.float32)
+        out[o] = acc
+    return np.moveaxis(out, 0, axis)
+
+
+@pytest.mark.parametrize("kind", sorted(KINDS))
+def test_host_tables_reproduce_the_port_bit_for_bit(b2, oracle, kind):
+    """No GPU needed: the gather tables the product's host code derives (b2_resize_axis_table: what the two kernels are
+    fed) applied in numpy float32 with the kernels' operation order give exactly the bytes of the restated port, which
+    walks scanlines through a ring buffer and scatters when down-sampling."""
+    rng = np.random.default_rng(30 + kind)
+    for (iw, ih), (ow, oh) in [((62, 33), (31, 17)), ((31, 17), (62, 33)), ((50, 21), (69, 12)), ((19, 46), (18, 100)), ((124, 66), (93, 50)), ((40, 9), (7, 5)), ((40, 30), (40, 15)), ((25, 30), (60, 30))]:
+        src = _src(rng, kind, iw, ih)
+        maxv = np.float32(65535.0 if src.dtype == np.uint16 else 255.0)
+        dec = (src.astype(np.float32) / maxv).astype(np.float32)                     # decode: IEEE division
+        tmp = _gather(dec, _axis_table(kind, iw, ow), iw, axis=1)     # an axis that keeps its size is filtered too (scale 1)
+        acc = _gather(tmp, _axis_table(kind, ih, oh), ih, axis=0)
+        enc = (np.clip(acc, np.float32(0), np.float32(1)) * maxv + np.float32(0.5)).astype(np.float32)
+        got = enc.astype(np.int64).astype(src.dtype)                                    # truncation
+        want = oracle.resizeImage(kind, src, ow, oh)
+        assert np.array_equal(got, want), (KINDS[kind], (iw, ih), (ow, oh), int((got != want).sum()))
